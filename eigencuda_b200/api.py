@@ -1,0 +1,259 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+Same names, argument meaning and error behaviour as `eigencuda::CudaPipeline`
+(reference include/cudapipeline.hpp:20-42, src/cudapipeline.cc:5-32) and `eigencuda::CudaMatrix`
+(reference include/cudamatrix.hpp:27-60, src/cudamatrix.cc:20-79), with `numpy` float64
+Fortran-ordered arrays standing where the C++ API has `Eigen::MatrixXd` (column-major, leading
+dimension = rows).  Everything goes through the C ABI (include/eigencuda_b200.h); nothing is
+computed in Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+
+Index = int  # `using Index = Eigen::Index`, include/cudamatrix.hpp:24
+
+
+def _as_eigen(a):
+    """Column-major float64 view/copy of `a`, like the storage of an Eigen::MatrixXd."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim != 2:
+        raise ValueError("expected a 2-D matrix")
+    return np.asfortranarray(a)
+
+
+def count_available_gpus():
+    """reference include/cudamatrix.hpp:25, src/cudamatrix.cc:14-18 (without the inverted ternary)."""
+    return int(lib.ec_device_count())
+
+
+class CudaMatrix:
+    """reference include/cudamatrix.hpp:27-60.
+
+    CudaMatrix(matrix, stream)        -> allocate + async H2D      (src/cudamatrix.cc:20-31)
+    CudaMatrix(nrows, ncols, stream)  -> allocate, uninitialised   (src/cudamatrix.cc:33-37)
+    Move-only in C++; here the handle is owned by the Python object and freed on `close`/GC.
+    """
+
+    def __init__(self, *args):
+        self._h = C.c_void_p()
+        if len(args) == 2:
+            matrix, stream = args
+            m = _as_eigen(matrix)
+            check(lib.ec_matrix_create_from_host(_stream_arg(stream), m.ctypes.data, m.shape[0],
+                                                 m.shape[1], C.byref(self._h)))
+        elif len(args) == 3:
+            nrows, ncols, stream = args
+            check(lib.ec_matrix_alloc(_stream_arg(stream), int(nrows), int(ncols), C.byref(self._h)))
+        else:
+            raise TypeError("CudaMatrix(matrix, stream) or CudaMatrix(nrows, ncols, stream)")
+
+    def rows(self):
+        return int(lib.ec_matrix_rows(self._h))
+
+    def cols(self):
+        return int(lib.ec_matrix_cols(self._h))
+
+    def size(self):
+        return int(lib.ec_matrix_size(self._h))
+
+    def data(self):
+        """Device address of the first element (double*)."""
+        return lib.ec_matrix_data(self._h) or 0
+
+    def copy_to_gpu(self, A):
+        """reference src/cudamatrix.cc:47-51: async H2D into the existing buffer; `A` is reusable
+        as soon as the call returns."""
+        a = _as_eigen(A)
+        check(lib.ec_matrix_upload(self._h, a.ctypes.data, a.size))
+
+    def to_eigen(self):
+        """`operator Eigen::MatrixXd() const`, reference src/cudamatrix.cc:39-45: blocking D2H."""
+        out = np.empty((self.rows(), self.cols()), dtype=np.float64, order="F")
+        check(lib.ec_matrix_download(self._h, out.ctypes.data))
+        return out
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.to_eigen()
+        return a if dtype is None else a.astype(dtype)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.ec_matrix_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _stream_arg(stream):
+    if isinstance(stream, CudaPipeline):
+        return stream.get_stream()
+    return C.c_void_p(int(stream) if stream else 0)
+
+
+class CudaPipeline:
+    """reference include/cudapipeline.hpp:20-42.  Owns one stream (no cuBLAS handle: the products
+    are launches of this package's own sm_100a kernels).  Non-copyable, like the reference."""
+
+    def __init__(self, device=-1, stream=None):
+        self._h = C.c_void_p()
+        if stream is None:
+            check(lib.ec_pipeline_create(int(device), C.byref(self._h)))
+        else:
+            check(lib.ec_pipeline_create_on_stream(int(device), C.c_void_p(int(stream)), C.byref(self._h)))
+
+    def __copy__(self):
+        raise TypeError("CudaPipeline is not copyable (reference include/cudapipeline.hpp:28-29)")
+
+    __deepcopy__ = __copy__
+
+    def get_stream(self):
+        """reference include/cudapipeline.hpp:34.  The cudaStream_t as an integer address."""
+        return C.c_void_p(lib.ec_pipeline_stream(self._h))
+
+    def device(self):
+        return int(lib.ec_pipeline_device(self._h))
+
+    def synchronize(self):
+        check(lib.ec_pipeline_synchronize(self._h))
+
+    def gemm(self, A, B, Cm):
+        """reference src/cudapipeline.cc:17-32: C = A * B; raises (std::runtime_error there,
+        EigenCudaError(RuntimeError) here) when A.cols() != B.rows(), before any device work."""
+        check(lib.ec_gemm(self._h, A._h, B._h, Cm._h))
+
+    # ---- additive API: the parameters the reference hard-codes ----
+    def dgemm(self, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, Cp, ldc):
+        """Raw device-pointer form of the cublasDgemm call at reference src/cudapipeline.cc:29-31."""
+        check(lib.ec_dgemm(self._h, int(transa), int(transb), m, n, k, float(alpha), int(A), lda,
+                           int(B), ldb, float(beta), int(Cp), ldc))
+
+    def dgemm_strided_batched(self, transa, transb, m, n, k, alpha, A, lda, sa, B, ldb, sb, beta,
+                              Cp, ldc, sc, batch):
+        check(lib.ec_dgemm_strided_batched(self._h, int(transa), int(transb), m, n, k, float(alpha),
+                                           int(A), lda, sa, int(B), ldb, sb, float(beta), int(Cp),
+                                           ldc, sc, batch))
+
+    def tensor_stream(self, kind, F, tensor, results=None):
+        """The reference's streaming loop (README.md:62-66, src/tests/test_dot.cc:81-85) as one
+        overlapped job.  `tensor` is a sequence of equally-shaped matrices (a Python list of
+        Fortran-ordered float64 arrays == std::vector<Eigen::MatrixXd>), `F` the fixed matrix.
+        Returns the list of results; `results` may supply preallocated outputs."""
+        F = _as_eigen(F)
+        ts = [_as_eigen(t) for t in tensor]
+        n = len(ts)
+        if n == 0:
+            return []
+        t_rows, t_cols = ts[0].shape
+        if any(t.shape != (t_rows, t_cols) for t in ts):
+            raise ValueError("all tensor elements must have the same shape")
+        r_shape = result_shape(kind, F.shape, (t_rows, t_cols))
+        if results is None:
+            results = [np.empty(r_shape, dtype=np.float64, order="F") for _ in range(n)]
+        in_ptrs = (C.c_void_p * n)(*[t.ctypes.data for t in ts])
+        out_ptrs = (C.c_void_p * n)(*[r.ctypes.data for r in results])
+        check(lib.ec_tensor_stream_run(self._h, int(kind), F.ctypes.data, F.shape[0], F.shape[1],
+                                       in_ptrs, out_ptrs, n, t_rows, t_cols))
+        return results
+
+    def right_multiply(self, tensor, F):
+        """results[i] = tensor[i] * F -- the order the reference's README/test use."""
+        return self.tensor_stream(_lib.EC_STREAM_RIGHT, F, tensor)
+
+    def left_multiply(self, F, tensor, transpose=False):
+        """results[i] = F * tensor[i]  (or F^T * tensor[i])."""
+        return self.tensor_stream(_lib.EC_STREAM_LEFT_T if transpose else _lib.EC_STREAM_LEFT, F, tensor)
+
+    def basis_transform(self, F, tensor):
+        """results[i] = F^T * tensor[i] * F  (BASELINE.json config 4; two products, the
+        intermediate never leaves the device)."""
+        return self.tensor_stream(_lib.EC_STREAM_BASIS, F, tensor)
+
+    def tensor_stream_raw(self, kind, F_ptr, f_rows, f_cols, in_ptrs, out_ptrs, count, t_rows, t_cols):
+        """Pointer-level form: `F_ptr` may be a host or a device address (the latter after the
+        multi-GPU broadcast), `in_ptrs`/`out_ptrs` ctypes arrays of host addresses."""
+        check(lib.ec_tensor_stream_run(self._h, int(kind), int(F_ptr), f_rows, f_cols, in_ptrs,
+                                       out_ptrs, count, t_rows, t_cols))
+
+    def tensor_stream_device(self, kind, F_dev, f_rows, f_cols, tensor_dev, results_dev, count,
+                             t_rows, t_cols):
+        check(lib.ec_tensor_stream_run_device(self._h, int(kind), int(F_dev), f_rows, f_cols,
+                                              int(tensor_dev), int(results_dev), count, t_rows, t_cols))
+
+    def set_stream_config(self, chunk_matrices=0, ring_depth=0, staging_threads=0):
+        check(lib.ec_pipeline_set_stream_config(self._h, chunk_matrices, ring_depth, staging_threads))
+
+    def fill_uniform(self, seed, first_id, dst, count, batch=1):
+        check(lib.ec_fill_uniform_batched(self._h, seed, first_id, int(dst), count, batch))
+
+    def launch_count(self):
+        return int(lib.ec_pipeline_launch_count(self._h))
+
+    def last_kernel(self):
+        return lib.ec_pipeline_last_kernel(self._h).decode()
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.ec_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def result_shape(kind, f_shape, t_shape):
+    """Shape of one result of a tensor-stream job; raises like the reference's gemm on an inner
+    dimension mismatch (reference src/cudapipeline.cc:26-28)."""
+    (fr, fc), (tr, tc) = f_shape, t_shape
+    if kind == _lib.EC_STREAM_RIGHT:
+        ok, shape = tc == fr, (tr, fc)
+    elif kind == _lib.EC_STREAM_LEFT:
+        ok, shape = fc == tr, (fr, tc)
+    elif kind == _lib.EC_STREAM_LEFT_T:
+        ok, shape = fr == tr, (fc, tc)
+    elif kind == _lib.EC_STREAM_BASIS:
+        ok, shape = fr == tr and tc == fr, (fc, fc)
+    else:
+        raise ValueError(f"unknown tensor-stream kind {kind}")
+    if not ok:
+        raise _lib.EigenCudaError(_lib.EC_ERR_SHAPE, "Shape mismatch in Cublas gemm")
+    return shape
+
+
+class PinnedBuffer:
+    """Page-locked host memory (what reference CHANGELOG.md:32 says 0.1.0 defaulted to), exposed
+    as a numpy array; DMA'd directly by the tensor-stream engine without staging."""
+
+    def __init__(self, shape, order="F"):
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        n = int(np.prod(self.shape))
+        self._ptr = C.c_void_p()
+        check(lib.ec_host_alloc(max(n, 1) * 8, C.byref(self._ptr)))
+        buf = (C.c_double * max(n, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.float64, count=n).reshape(self.shape, order=order)
+
+    @property
+    def ptr(self):
+        return self._ptr.value
+
+    def close(self):
+        if self._ptr:
+            self.array = None
+            lib.ec_host_free(self._ptr)
+            self._ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,451 @@
+// eigencuda_b200/csrc/dgemm_kernels.cuh -- hand-written sm_100a FP64 GEMM kernels.
+//
+// These kernels replace the one device computation of the reference, the cublasDgemm call in
+// CudaPipeline::gemm (reference src/cudapipeline.cc:29-31): C = alpha * op(A) * op(B) + beta * C,
+// FP64, column-major.  Nothing here is derived from cuBLAS or from the reference's sources.
+//
+//   dgemm_tma_dmma_kernel   the hot kernel.  Persistent (one CTA per SM, static tile schedule),
+//                           warp-specialised: one producer warp feeds a 5-stage smem ring with
+//                           TMA (cp.async.bulk.tensor, 128B swizzle) signalled through
+//                           mbarriers; eight consumer warps hold a 128x128 C tile in registers
+//                           (64x32 per warp) and issue FP64 DMMA (mma.sync.m8n8k4.f64 -- the only
+//                           FP64 tensor shape sm_100a has: every larger PTX shape lowers to
+//                           DMMA.8x8x4 in SASS).  All four op(A)/op(B) combinations are served by
+//                           two smem layouts per operand ("K-major" and "MN-major"), both read
+//                           with conflict-free LDS.128.  Batched over a third tensor-map
+//                           dimension for the tensor-stream job (one launch per chunk).
+//   dgemm_simt_kernel       generic fallback for what TMA cannot address (odd leading
+//                           dimensions, unaligned bases) and for tiny problems such as the
+//                           README's 3x2 * 2x2: register-tiled FP64 FMA, bounds-checked.
+//   scale_kernel            C = beta * C for the k == 0 / alpha == 0 corner.
+//   fill_uniform_kernel     counter-based synthetic inputs, bit-identical to the CPU oracle.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ec {
+
+// ------------------------------------------------------------------------------------------
+// Tile configuration of the hot kernel
+// ------------------------------------------------------------------------------------------
+constexpr int BM = 128;            // C tile rows per CTA
+constexpr int BN = 128;            // C tile cols per CTA
+constexpr int BK = 16;             // k extent per stage: 16 doubles = 128 B = one swizzle span
+constexpr int STAGES = 5;          // 5 x 32 KiB ring
+constexpr int CONSUMER_WARPS = 8;  // 2 (m) x 4 (n), warp tile 64 x 32
+constexpr int WM = 64, WN = 32;
+// Three warpgroups: two of consumers, one whose first warp is the producer.  The register file
+// is allocated in 4-warp units anyway (9 warps cost the same as 12: 168 regs/thread), so the
+// producer group gives its registers away with setmaxnreg and the consumers grow to 232.
+constexpr int GEMM_THREADS = (CONSUMER_WARPS + 4) * 32;
+constexpr int PRODUCER_REGS = 40, CONSUMER_REGS = 232;
+constexpr int OPERAND_STAGE_BYTES = BM * BK * 8;             // 16 KiB (BM == BN)
+constexpr int STAGE_BYTES = 2 * OPERAND_STAGE_BYTES;         // 32 KiB
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+struct GemmParams {
+  int64_t M, N, K;
+  int64_t batch;
+  double alpha, beta;
+  double *C;
+  int64_t ldc, stride_c;
+  int tiles_m, tiles_n;
+  int64_t total_tiles;
+  int a_batched, b_batched;  // 0: operand shared by every problem of the batch (coordinate 0)
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+// 3D tiled TMA load, completion reported as transaction bytes on an mbarrier.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  lane = 4*g + c:
+// A fragment = A[g][c], B fragment = B[c][g], D fragment = D[g][2c], D[g][2c+1].
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
+}
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
+}
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared-memory operand layouts (per stage, per operand: 128 "mn" x 16 "k" doubles = 16 KiB).
+//
+// K-major (memory-contiguous along k: op(A)=A^T, op(B)=B): ONE TMA box {16 k, 128 mn}; row mn is
+//   128 B, the 16-byte chunk index is XORed with (mn & 7) by the 128B swizzle:
+//       off(mn,k) = mn*128 + (((k>>1) ^ (mn&7)) << 4) + (k&1)*8
+// MN-major (memory-contiguous along m or n: op(A)=A, op(B)=B^T): EIGHT TMA boxes {16 mn, 16 k},
+//   sub-tile j = mn>>4 at j*2048, row k is 128 B, chunk XORed with (k & 7):
+//       off(mn,k) = (mn>>4)*2048 + k*128 + ((((mn&15)>>1) ^ (k&7)) << 4) + (mn&1)*8
+//
+// One k8 step issues, per 8x8 output block, two DMMAs: "even" takes k = {0,2,4,6} on fragment
+// lanes c = 0..3 and "odd" takes k = {1,3,5,7}.  Any permutation of k inside a DMMA is legal as
+// long as both operands agree, and any permutation of the 8 rows (columns) a fragment lane g
+// stands for is legal as long as the epilogue writes C accordingly.  The permutations below are
+// what makes every LDS.128 bank-conflict-free (each quarter-warp covers 8 distinct 16 B chunks):
+//   K-major : lane (g,c) loads 16 B = k {2c, 2c+1} of row  8*blk + pi(g),  pi(g) = (g>>1) + 4*(g&1)
+//             -> .x feeds the even DMMA, .y the odd DMMA of block blk.
+//   MN-major: lane (g,c) loads 16 B = mn {2g, 2g+1} of 16-block jb at k = 2c (then at k = 2c+1)
+//             -> .x is a fragment of block 2*jb (rows 16*jb + 2g), .y of block 2*jb+1 (rows +1).
+// ------------------------------------------------------------------------------------------
+template <bool KMAJOR>
+__device__ __forceinline__ int frag_mn(int blk, int g) {
+  if (KMAJOR) return 8 * blk + (g >> 1) + 4 * (g & 1);
+  return 16 * (blk >> 1) + 2 * g + (blk & 1);
+}
+
+// Load the fragments of NBLK 8-wide blocks starting at warp offset `w0` (multiple of 16) for the
+// k8 step at kk (0 or 8).  fe[b] / fo[b]: even-k / odd-k fragment of block b.
+template <bool KMAJOR, int NBLK>
+__device__ __forceinline__ void load_frags(uint32_t base, int w0, int kk, int g, int c,
+                                           double (&fe)[NBLK], double (&fo)[NBLK]) {
+  if (KMAJOR) {
+    const int pg = (g >> 1) + 4 * (g & 1);
+    const uint32_t lane_off = (uint32_t)((w0 + pg) * 128 + ((((kk >> 1) + c) ^ pg) << 4));
+#pragma unroll
+    for (int b = 0; b < NBLK; ++b) {
+      double2 v = lds128(base + lane_off + b * 1024);
+      fe[b] = v.x;
+      fo[b] = v.y;
+    }
+  } else {
+    const int ke = kk + 2 * c, ko = ke + 1;
+    const uint32_t off_e = (uint32_t)((w0 >> 4) * 2048 + ke * 128 + ((g ^ (ke & 7)) << 4));
+    const uint32_t off_o = (uint32_t)((w0 >> 4) * 2048 + ko * 128 + ((g ^ (ko & 7)) << 4));
+#pragma unroll
+    for (int jb = 0; jb < NBLK / 2; ++jb) {
+      double2 ve = lds128(base + off_e + jb * 2048);
+      double2 vo = lds128(base + off_o + jb * 2048);
+      fe[2 * jb] = ve.x;
+      fe[2 * jb + 1] = ve.y;
+      fo[2 * jb] = vo.x;
+      fo[2 * jb + 1] = vo.y;
+    }
+  }
+}
+
+// Producer side: fill one operand's stage.  K-major: one box; MN-major: eight boxes.
+template <bool KMAJOR>
+__device__ __forceinline__ void tma_fill_operand(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                                 int mn0, int k0, int b) {
+  if (KMAJOR) {
+    tma_load_3d(dst, map, bar, k0, mn0, b);
+  } else {
+#pragma unroll
+    for (int j = 0; j < BM / 16; ++j) tma_load_3d(dst + j * 2048, map, bar, mn0 + 16 * j, k0, b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// The hot kernel
+// ------------------------------------------------------------------------------------------
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap tmA,
+                          const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled TMA destinations need 1024-byte alignment.
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES]
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);                // one arrive.expect_tx by the producer
+      mbar_init(empty_bar(s), CONSUMER_WARPS);  // one arrive per consumer warp
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == CONSUMER_WARPS && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  __syncthreads();
+
+  const int kblocks = (int)((p.K + BK - 1) / BK);
+  const int tiles_per_problem = p.tiles_m * p.tiles_n;
+
+  if (warp >= CONSUMER_WARPS) {
+    // ===================== TMA producer (one elected lane of the third warpgroup) ===========
+    setmaxnreg_dec<PRODUCER_REGS>();
+    if (warp == CONSUMER_WARPS && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int b = (int)(tile / tiles_per_problem);
+        const int r = (int)(tile - (int64_t)b * tiles_per_problem);
+        const int m0 = (r % p.tiles_m) * BM;
+        const int n0 = (r / p.tiles_m) * BN;
+        const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          const uint32_t sA = smem_base + stage * STAGE_BYTES;
+          const uint32_t sB = sA + OPERAND_STAGE_BYTES;
+          tma_fill_operand<A_KMAJOR>(sA, &tmA, full_bar(stage), m0, kb * BK, ba);
+          tma_fill_operand<B_KMAJOR>(sB, &tmB, full_bar(stage), n0, kb * BK, bb);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== DMMA consumers =====================
+  setmaxnreg_inc<CONSUMER_REGS>();
+  const int g = lane >> 2, c = lane & 3;
+  const int wm0 = (warp & 1) * WM;   // warp's row offset inside the CTA tile
+  const int wn0 = (warp >> 1) * WN;  // warp's column offset
+  constexpr int MB = WM / 8;         // 8 row blocks
+  constexpr int NB = WN / 8;         // 4 column blocks
+
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int b = (int)(tile / tiles_per_problem);
+    const int r = (int)(tile - (int64_t)b * tiles_per_problem);
+    const int m0 = (r % p.tiles_m) * BM;
+    const int n0 = (r / p.tiles_m) * BN;
+
+    double acc[MB][NB][2];
+#pragma unroll
+    for (int i = 0; i < MB; ++i)
+#pragma unroll
+      for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kb = 0; kb < kblocks; ++kb) {
+      mbar_wait(full_bar(stage), phase);
+      const uint32_t sA = smem_base + stage * STAGE_BYTES;
+      const uint32_t sB = sA + OPERAND_STAGE_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < BK; kk += 8) {
+        double ae[MB], ao[MB], be[NB], bo[NB];
+        load_frags<A_KMAJOR, MB>(sA, wm0, kk, g, c, ae, ao);
+        load_frags<B_KMAJOR, NB>(sB, wn0, kk, g, c, be, bo);
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+#pragma unroll
+          for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], ae[i], be[j]);
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+#pragma unroll
+          for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], ao[i], bo[j]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(stage));
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+
+    // ---- epilogue: registers -> global, C = alpha*acc + beta*C, bounds-predicated ----
+    double *Cb = p.C + (int64_t)b * p.stride_c;
+    const bool use_beta = (p.beta != 0.0);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int64_t col = n0 + wn0 + frag_mn<B_KMAJOR>(j, 2 * c + e);
+        if (col < p.N) {
+          double *Ccol = Cb + col * p.ldc;
+#pragma unroll
+          for (int i = 0; i < MB; ++i) {
+            const int64_t row = m0 + wm0 + frag_mn<A_KMAJOR>(i, g);
+            if (row < p.M) {
+              double v = p.alpha * acc[i][j][e];
+              if (use_beta) v += p.beta * Ccol[row];
+              Ccol[row] = v;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic fallback: register-tiled FP64 FMA, any shape / leading dimension / alignment.
+// 64x64 C tile, 256 threads, 4x4 per thread, k step 16.
+// ------------------------------------------------------------------------------------------
+constexpr int SB = 64, SK = 16, SIMT_THREADS = 256;
+
+struct SimtParams {
+  int64_t M, N, K, batch;
+  double alpha, beta;
+  const double *A;
+  int64_t lda, stride_a;
+  const double *B;
+  int64_t ldb, stride_b;
+  double *C;
+  int64_t ldc, stride_c;
+  int transa, transb;
+  int tiles_m, tiles_n;
+  int64_t total_tiles;
+};
+
+__global__ void __launch_bounds__(SIMT_THREADS) dgemm_simt_kernel(const SimtParams p) {
+  __shared__ double As[SK][SB + 1];  // [k][m]
+  __shared__ double Bs[SK][SB + 1];  // [k][n]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int tiles_per_problem = p.tiles_m * p.tiles_n;
+  for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int64_t b = tile / tiles_per_problem;
+    const int r = (int)(tile - b * tiles_per_problem);
+    const int64_t m0 = (int64_t)(r % p.tiles_m) * SB, n0 = (int64_t)(r / p.tiles_m) * SB;
+    const double *A = p.A + b * p.stride_a;
+    const double *B = p.B + b * p.stride_b;
+    double *C = p.C + b * p.stride_c;
+    double acc[4][4] = {};
+    for (int64_t k0 = 0; k0 < p.K; k0 += SK) {
+      // cooperative, bounds-checked loads; index order chosen so the contiguous memory
+      // direction is the fastest-varying thread index for each transpose case
+      for (int idx = threadIdx.x; idx < SB * SK; idx += SIMT_THREADS) {
+        int mi, ki;
+        if (!p.transa) { mi = idx % SB; ki = idx / SB; } else { ki = idx % SK; mi = idx / SK; }
+        const int64_t gm = m0 + mi, gk = k0 + ki;
+        double v = 0.0;
+        if (gm < p.M && gk < p.K) v = p.transa ? A[gm * p.lda + gk] : A[gk * p.lda + gm];
+        As[ki][mi] = v;
+      }
+      for (int idx = threadIdx.x; idx < SB * SK; idx += SIMT_THREADS) {
+        int ni, ki;
+        if (!p.transb) { ki = idx % SK; ni = idx / SK; } else { ni = idx % SB; ki = idx / SB; }
+        const int64_t gn = n0 + ni, gk = k0 + ki;
+        double v = 0.0;
+        if (gn < p.N && gk < p.K) v = p.transb ? B[gk * p.ldb + gn] : B[gn * p.ldb + gk];
+        Bs[ki][ni] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < SK; ++kk) {
+        double a[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[kk][tx + 16 * i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][ty + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t col = n0 + ty + 16 * j;
+      if (col >= p.N) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t row = m0 + tx + 16 * i;
+        if (row >= p.M) continue;
+        double v = p.alpha * acc[i][j];
+        if (p.beta != 0.0) v += p.beta * C[col * p.ldc + row];
+        C[col * p.ldc + row] = v;
+      }
+    }
+  }
+}
+
+// C = beta * C (beta == 0 writes zeros without reading), m x n, batched.
+__global__ void scale_kernel(double *C, int64_t m, int64_t n, int64_t ldc, int64_t stride_c,
+                             int64_t batch, double beta) {
+  const int64_t per = m * n, total = per * batch;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / per, r = idx - b * per;
+    double *ptr = C + b * stride_c + (r / m) * ldc + (r % m);
+    *ptr = (beta == 0.0) ? 0.0 : beta * *ptr;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Synthetic inputs: same integer recipe as oracle/dgemm_oracle.c (oracle_uniform_at).
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+
+__global__ void fill_uniform_kernel(uint64_t seed, uint64_t first_id, double *dst, int64_t count,
+                                    int64_t batch) {
+  const int64_t total = count * batch;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / count, i = idx - b * count;
+    const uint64_t key = splitmix64(seed ^ splitmix64(first_id + (uint64_t)b + 0x632BE59BD9B4E019ULL));
+    const uint64_t rnd = splitmix64(key + (uint64_t)i * 0xD1342543DE82EF95ULL);
+    const double u = (double)(rnd >> 11) * (1.0 / 9007199254740992.0);
+    dst[idx] = 2.0 * u - 1.0;
+  }
+}
+
+}  // namespace ec

@@ -1,0 +1,173 @@
+/*
+ * eigencuda_b200.h -- the C ABI of the B200-native replacement for EigenCuda's hot path.
+ *
+ * This is the drop-in boundary: plain pointers, sizes and opaque handles; no C++ types, no torch
+ * types, no exceptions.  include/cudamatrix.hpp and include/cudapipeline.hpp (source-compatible
+ * with the reference's headers of the same names) are thin inline wrappers over these functions,
+ * and eigencuda_b200/ (Python) binds the same symbols through ctypes.
+ *
+ * Every entry point cites the reference interface (path:line under NLESC-JCER/EigenCuda) it
+ * replaces.  All matrices are FP64, column-major, contiguous unless a leading dimension is given.
+ * Status codes: 0 = ok; nonzero = error, with a message available from ec_last_error_string()
+ * (thread-local).  Handles are thread-compatible (one host thread at a time per pipeline), as in
+ * the reference, which has no locks either.
+ *
+ * There is no CPU fallback behind this ABI: every compute entry point launches hand-written
+ * sm_100a kernels (eigencuda_b200/csrc/) and fails with EC_ERR_CUDA when no B200 is present.
+ */
+#ifndef EIGENCUDA_B200_H
+#define EIGENCUDA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ec_pipeline ec_pipeline; /* replaces class CudaPipeline, include/cudapipeline.hpp:20-42 */
+typedef struct ec_matrix ec_matrix;     /* replaces class CudaMatrix,   include/cudamatrix.hpp:27-60   */
+
+enum {
+  EC_OK = 0,
+  EC_ERR_SHAPE = 1,   /* "Shape mismatch in Cublas gemm", src/cudapipeline.cc:26-28          */
+  EC_ERR_NOMEM = 2,   /* throw_if_not_enough_memory_in_gpu, src/cudamatrix.cc:63-79          */
+  EC_ERR_COPY = 3,    /* "Error copy arrays to device", src/cudamatrix.cc:28-30              */
+  EC_ERR_CUDA = 4,    /* any other CUDA failure (the reference swallows these, :5-12)        */
+  EC_ERR_ARG = 5,     /* null handle / negative size / bad enum                              */
+  EC_ERR_UNSUPPORTED = 6
+};
+
+enum { EC_OP_N = 0, EC_OP_T = 1 };
+
+/* Arithmetic backend for the GEMM kernels.  EC_BACKEND_FP64_DMMA is the native path (FP64
+ * mma.sync fragments, parity bar 1e-12 relative Frobenius).  EC_BACKEND_OZAKI_I8 is the selectable
+ * int8 tcgen05 emulation with a looser, explicitly stated bound. */
+enum { EC_BACKEND_FP64_DMMA = 0, EC_BACKEND_OZAKI_I8 = 1 };
+
+/* Tensor-stream job kinds (ec_tensor_stream_run): what each tensor element T_i is multiplied by.
+ * RIGHT is the order the reference itself uses (gemm(cuma_B, cuma_A, cuma_C) with cuma_B the
+ * streamed element, README.md:62-66 / src/tests/test_dot.cc:81-85). */
+enum {
+  EC_STREAM_RIGHT = 0,   /* R_i = T_i * F                                                 */
+  EC_STREAM_LEFT = 1,    /* R_i = F * T_i                                                 */
+  EC_STREAM_LEFT_T = 2,  /* R_i = F^T * T_i            (BASELINE.json config 4, A^T*B)    */
+  EC_STREAM_BASIS = 3    /* R_i = F^T * T_i * F        (BASELINE.json config 4, A^T*M*A)  */
+};
+
+/* ---- library / device --------------------------------------------------------------------- */
+
+const char *ec_version(void);
+const char *ec_last_error_string(void);
+
+/* count_available_gpus(), include/cudamatrix.hpp:25, src/cudamatrix.cc:14-18.  Returns the device
+ * count, or 0 on error (the reference's ternary is inverted and returns garbage on error). */
+int64_t ec_device_count(void);
+
+/* ---- pipeline: CudaPipeline, include/cudapipeline.hpp:20-42 ------------------------------- */
+
+/* CudaPipeline::CudaPipeline(), include/cudapipeline.hpp:22-25: one stream per pipeline (the
+ * reference also creates a cuBLAS handle; there is none here).  device < 0 = current device. */
+int ec_pipeline_create(int device, ec_pipeline **out);
+/* Same, but runs on a caller-owned stream (e.g. a framework's current stream); not destroyed. */
+int ec_pipeline_create_on_stream(int device, void *cuda_stream, ec_pipeline **out);
+/* CudaPipeline::~CudaPipeline(), src/cudapipeline.cc:5-11. */
+int ec_pipeline_destroy(ec_pipeline *p);
+/* CudaPipeline::get_stream(), include/cudapipeline.hpp:34.  Returns the cudaStream_t. */
+void *ec_pipeline_stream(const ec_pipeline *p);
+/* Address of the stored cudaStream_t (get_stream() returns a const reference). */
+const void *ec_pipeline_stream_ref(const ec_pipeline *p);
+int ec_pipeline_device(const ec_pipeline *p);
+int ec_pipeline_synchronize(ec_pipeline *p);
+int ec_pipeline_set_backend(ec_pipeline *p, int backend);
+int ec_pipeline_get_backend(const ec_pipeline *p);
+
+/* ---- device matrix: CudaMatrix, include/cudamatrix.hpp:27-60 ------------------------------ */
+
+/* CudaMatrix(Index nrows, Index ncols, const cudaStream_t&), src/cudamatrix.cc:33-37:
+ * allocate rows*cols doubles on the stream's device, contents uninitialised.
+ * EC_ERR_NOMEM when the request exceeds free device memory (src/cudamatrix.cc:63-79). */
+int ec_matrix_alloc(void *cuda_stream, int64_t rows, int64_t cols, ec_matrix **out);
+/* CudaMatrix(const Eigen::MatrixXd&, const cudaStream_t&), src/cudamatrix.cc:20-31:
+ * allocate + asynchronous H2D of rows*cols doubles.  EC_ERR_COPY if the copy cannot be issued.
+ * `host` may be pageable; it is reusable as soon as the call returns. */
+int ec_matrix_create_from_host(void *cuda_stream, const double *host, int64_t rows, int64_t cols,
+                               ec_matrix **out);
+/* ~CudaMatrix (the unique_ptr deleter, include/cudamatrix.hpp:46,55-56). */
+int ec_matrix_free(ec_matrix *m);
+/* CudaMatrix::copy_to_gpu(const Eigen::MatrixXd&), src/cudamatrix.cc:47-51: asynchronous H2D of
+ * `count` doubles into the existing buffer, on the matrix's stream; `host` reusable on return.
+ * Unlike the reference (Appendix A #5) count > rows*cols is rejected with EC_ERR_ARG. */
+int ec_matrix_upload(ec_matrix *m, const double *host, int64_t count);
+/* CudaMatrix::operator Eigen::MatrixXd() const, src/cudamatrix.cc:39-45: D2H of the whole
+ * matrix; the result is complete in `host` when the call returns. */
+int ec_matrix_download(const ec_matrix *m, double *host);
+/* rows()/cols()/size()/data(), include/cudamatrix.hpp:29-32. */
+int64_t ec_matrix_rows(const ec_matrix *m);
+int64_t ec_matrix_cols(const ec_matrix *m);
+int64_t ec_matrix_size(const ec_matrix *m);
+double *ec_matrix_data(const ec_matrix *m);
+
+/* ---- the hot op: CudaPipeline::gemm, src/cudapipeline.cc:17-32 ---------------------------- */
+
+/* gemm(A, B, C): C = A * B.  EC_ERR_SHAPE when A.cols != B.rows, before any device work
+ * (src/cudapipeline.cc:26-28).  C's shape is not validated, as in the reference: its rows() is
+ * the leading dimension of the output (src/cudapipeline.cc:31). */
+int ec_gemm(ec_pipeline *p, const ec_matrix *A, const ec_matrix *B, ec_matrix *C);
+
+/* The cublasDgemm call itself, src/cudapipeline.cc:29-31, with the parameters the reference
+ * hard-codes opened up: C = alpha * op(A) * op(B) + beta * C on device pointers, 64-bit
+ * dimensions (the reference narrows to int, Appendix A #4).  op(A) is m x k, op(B) is k x n. */
+int ec_dgemm(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha,
+             const double *A, int64_t lda, const double *B, int64_t ldb, double beta, double *C,
+             int64_t ldc);
+
+/* The same product for `batch` independent problems at fixed element strides (stride 0 =
+ * operand shared by all problems): one launch for a chunk of the matrix tensor against the
+ * fixed operand.  Resurrects the gemmBatched path CHANGELOG.md:24 records as removed. */
+int ec_dgemm_strided_batched(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
+                             int64_t k, double alpha, const double *A, int64_t lda,
+                             int64_t stride_a, const double *B, int64_t ldb, int64_t stride_b,
+                             double beta, double *C, int64_t ldc, int64_t stride_c, int64_t batch);
+
+/* ---- the streaming loop as one overlapped job --------------------------------------------- */
+
+/* README.md:58-66 / src/tests/test_dot.cc:77-85, the whole `for` loop:
+ *     for i: cuma_B.copy_to_gpu(tensor[i]); cuda_pip.gemm(...); results[i] = cuma_C;
+ * F is f_rows x f_cols, every tensor[i] is t_rows x t_cols, results[i] receives the product
+ * (shape by `kind`), all host pointers, column-major, ld = rows.  H2D, compute and D2H run on
+ * separate streams over a ring of device chunks; pinned/registered host buffers are DMA'd
+ * directly, pageable ones go through a pinned staging ring filled by worker threads.
+ * All results are complete in host memory when the call returns. */
+int ec_tensor_stream_run(ec_pipeline *p, int kind, const double *F, int64_t f_rows, int64_t f_cols,
+                         const double *const *tensor, double *const *results, int64_t count,
+                         int64_t t_rows, int64_t t_cols);
+/* Same job on a tensor that is already resident in device memory as `count` consecutive
+ * matrices (element stride t_rows*t_cols); results written to `results_dev` likewise. */
+int ec_tensor_stream_run_device(ec_pipeline *p, int kind, const double *F_dev, int64_t f_rows,
+                                int64_t f_cols, const double *tensor_dev, double *results_dev,
+                                int64_t count, int64_t t_rows, int64_t t_cols);
+/* Engine knobs: matrices per device chunk, ring depth, staging worker threads (0 = default). */
+int ec_pipeline_set_stream_config(ec_pipeline *p, int chunk_matrices, int ring_depth,
+                                  int staging_threads);
+
+/* ---- host memory + synthetic data helpers ------------------------------------------------- */
+
+/* Pinned host allocation (what CHANGELOG.md:32 records the reference once defaulted to). */
+int ec_host_alloc(size_t bytes, void **out);
+int ec_host_free(void *ptr);
+/* x = 2u-1, u in [0,1): splitmix64 on (seed, matrix_id, column-major index); bit-identical to
+ * oracle_fill_uniform.  Fills `count` doubles at device pointer dst. */
+int ec_fill_uniform(ec_pipeline *p, uint64_t seed, uint64_t matrix_id, double *dst, int64_t count);
+/* Same, `batch` matrices of `count` doubles each: matrix b gets matrix_id = first_id + b. */
+int ec_fill_uniform_batched(ec_pipeline *p, uint64_t seed, uint64_t first_id, double *dst,
+                            int64_t count, int64_t batch);
+/* Launch counter: number of kernels this library has launched on this pipeline since creation. */
+int64_t ec_pipeline_launch_count(const ec_pipeline *p);
+/* Name of the kernel variant the last ec_dgemm* on this pipeline dispatched to. */
+const char *ec_pipeline_last_kernel(const ec_pipeline *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EIGENCUDA_B200_H */

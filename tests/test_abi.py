@@ -1,0 +1,99 @@
+"""The C-ABI library loads and exports every symbol include/eigencuda_b200.h declares; error
+paths that must not need a GPU behave (not gpu: no compute calls here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "eigencuda_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ec_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = declared_symbols()
+    for must in ("ec_pipeline_create", "ec_pipeline_destroy", "ec_pipeline_stream", "ec_matrix_alloc",
+                 "ec_matrix_create_from_host", "ec_matrix_upload", "ec_matrix_download", "ec_gemm",
+                 "ec_dgemm", "ec_dgemm_strided_batched", "ec_tensor_stream_run", "ec_device_count"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    import eigencuda_b200._lib as L
+    lib = C.CDLL(L.LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+    # and the Python binding table covers the header exactly
+    assert sorted(L.SIGNATURES) == declared_symbols()
+
+
+def test_no_cublas_and_no_oracle_linked():
+    import eigencuda_b200._lib as L
+    out = subprocess.run(["ldd", L.LIB_PATH], capture_output=True, text=True).stdout
+    assert "cublas" not in out.lower(), out
+    assert "oracle" not in out.lower(), out
+    assert "libcuda.so" not in out, "must not hard-link the driver (loads without a GPU)"
+
+
+def test_product_sources_do_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "eigencuda_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                for line in text.splitlines():
+                    s = line.strip()
+                    if s.startswith(("import ", "from ", "#include")):
+                        assert "oracle" not in s, (f, s)
+    for f in ("cudamatrix.hpp", "cudapipeline.hpp", "eigencuda_b200.h"):
+        for line in open(os.path.join(ROOT, "include", f)):
+            if line.strip().startswith("#include"):
+                assert "oracle" not in line and "cublas" not in line, (f, line)
+
+
+def test_argument_errors_need_no_gpu():
+    import eigencuda_b200 as ec
+    from eigencuda_b200._lib import EC_ERR_ARG, lib
+    assert lib.ec_version().startswith(b"eigencuda_b200")
+    assert lib.ec_gemm(None, None, None, None) == EC_ERR_ARG
+    assert b"null" in lib.ec_last_error_string()
+    assert lib.ec_dgemm(None, 0, 0, 1, 1, 1, 1.0, None, 1, None, 1, 0.0, None, 1) == EC_ERR_ARG
+    assert lib.ec_matrix_upload(None, None, 0) == EC_ERR_ARG
+    assert lib.ec_pipeline_destroy(None) == 0 and lib.ec_matrix_free(None) == 0
+    assert ec.count_available_gpus() >= 0
+
+
+def test_fails_loudly_without_a_gpu():
+    import eigencuda_b200 as ec
+    if ec.count_available_gpus() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(ec.EigenCudaError):
+        ec.CudaPipeline()
+
+
+def test_missing_library_raises(tmp_path):
+    import eigencuda_b200._lib as L
+    with pytest.raises(RuntimeError, match="no CPU fallback|not built"):
+        L.load(str(tmp_path / "nope.so"))
+
+
+def test_cpp_headers_compile_against_the_abi(tmp_path):
+    """include/cudamatrix.hpp + cudapipeline.hpp: caller code written like the reference's tests
+    compiles unchanged (Eigen stand-in, since Eigen is not in the image)."""
+    exe = tmp_path / "test_dot_compat"
+    cmd = ["g++", "-std=c++14", "-O1", "-Wall", "-Werror", f"-I{ROOT}/include",
+           f"-I{ROOT}/oracle/eigen_standin", "-I/usr/local/cuda/include",
+           f"{ROOT}/tests/cpp/test_dot_compat.cc", "-o", str(exe),
+           f"-L{ROOT}/eigencuda_b200/lib", "-leigencuda_b200",
+           f"-Wl,-rpath,{ROOT}/eigencuda_b200/lib"]
+    if not os.path.exists("/usr/local/cuda/include/cuda_runtime_api.h"):
+        pytest.skip("CUDA headers not present")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr

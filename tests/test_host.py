@@ -1,0 +1,89 @@
+"""Host-side logic that needs no GPU: shapes, sharding, the 2-rank gloo path (not gpu)."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+import eigencuda_b200 as ec
+from eigencuda_b200 import shard
+from oracle import oracle_py as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_range_partitions_exactly():
+    for count in (0, 1, 3, 7, 4096, 4097):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard.shard_range(count, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == count
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and a <= b and c <= d
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard.shard_range(4, 4, 4)
+
+
+def test_result_shape_and_mismatch():
+    assert ec.result_shape(ec.EC_STREAM_RIGHT, (2, 2), (3, 2)) == (3, 2)      # README example
+    assert ec.result_shape(ec.EC_STREAM_LEFT, (4, 3), (3, 5)) == (4, 5)
+    assert ec.result_shape(ec.EC_STREAM_LEFT_T, (3, 4), (3, 5)) == (4, 5)
+    assert ec.result_shape(ec.EC_STREAM_BASIS, (6, 4), (6, 6)) == (4, 4)
+    with pytest.raises(ec.EigenCudaError):
+        ec.result_shape(ec.EC_STREAM_RIGHT, (5, 5), (3, 2))                   # test_dot.cc:92-103
+    with pytest.raises(RuntimeError):   # EigenCudaError is a RuntimeError, like std::runtime_error
+        ec.result_shape(ec.EC_STREAM_BASIS, (6, 4), (6, 5))
+
+
+def test_pipeline_is_not_copyable():
+    import copy
+    p = object.__new__(ec.CudaPipeline)
+    with pytest.raises(TypeError):
+        copy.copy(p)
+
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r})
+    import numpy as np, torch, torch.distributed as dist
+    from eigencuda_b200 import shard
+    from oracle import oracle_py as orc
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    count, n = 11, 12
+    # rank 0 owns the fixed operand; everyone else starts with garbage and receives it
+    F = torch.from_numpy(orc.fill_uniform(orc.SEED, 0, (n, n)).copy()) if rank == 0 else torch.full((n, n), float("nan"), dtype=torch.float64)
+    shard.broadcast_fixed(F, src=0)
+    lo, hi = shard.shard_range(count, rank, world)
+    ts = [orc.fill_uniform(orc.SEED, i + 1, (n, n)) for i in range(lo, hi)]
+    # the sharded job itself (the oracle stands in for the GPU product in this CPU test)
+    res = orc.tensor_stream("right", F.numpy(), ts)
+    counts = shard.gather_counts(len(res))
+    assert sum(counts) == count and counts[rank] == hi - lo, counts
+    chk = torch.tensor([sum(float(r.sum()) for r in res)], dtype=torch.float64)
+    dist.all_reduce(chk)
+    if rank == 0:
+        Fh = orc.fill_uniform(orc.SEED, 0, (n, n))
+        want = sum(float((orc.fill_uniform(orc.SEED, i + 1, (n, n)) @ Fh).sum()) for i in range(count))
+        assert abs(chk.item() - want) < 1e-9, (chk.item(), want)
+        print("GLOO_OK", counts)
+    dist.destroy_process_group()
+""")
+
+
+def test_two_rank_gloo_shard_and_broadcast(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "GLOO_OK [6, 5]" in res.stdout or "GLOO_OK [5, 6]" in res.stdout, res.stdout
