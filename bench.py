@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: tensor-stream matrices/s and
+FP64 DGEMM TFLOP/s, vs roofline, next to a CPU product).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[2], the streaming pattern of the reference
+(README.md:62-66): `count` matrices T_i (n x n) against one fixed F (n x n), R_i = T_i * F, FP64,
+column-major.  Default 4096 x (512x512) PER GPU (weak scaling: the tensor shards into contiguous
+index ranges, no data-path collective; the fixed operand is broadcast once with NCCL).
+One "step" = one pass of the hot path over the rank's whole tensor.
+
+    value      matrices/s, whole job, inputs already resident in HBM (one batched-DGEMM launch
+               per step), CUDA events on the launching stream, max over ranks
+    e2e        the same metric through the C-ABI tensor-stream call with PINNED HOST buffers:
+               H2D of every T_i, the products, D2H of every R_i inside the timed region
+    roofline   dominant kernel = dgemm_tma_dmma (FP64 DMMA): achieved TFLOP/s vs FP64 peak.
+               MEASURED_PEAKS.json carries no FP64 figure, so `peak` is the datasheet-derived
+               148 SM x 128 flop/clk x 1.965 GHz = 37.2 TFLOP/s and the measured DMMA issue peak
+               of this box (tools/bin/peaks) is reported beside it.
+    cpu_baseline  numpy/OpenBLAS dgemm on all host cores over a bounded sample of the same
+               workload (kind "port": Eigen itself is not installed in the image)
+    dgemm      BASELINE.json configs[1]: square FP64 DGEMM TFLOP/s on 1 GPU at a few n
+
+--impl reference times the UNMODIFIED reference (oracle/_ref: its own sources compiled against
+cuBLAS) running its stock streaming loop on the same GPU from pageable host memory, on a bounded
+sample of the same workload; where oracle/_ref cannot run it falls back to the CPU oracle port.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FP64_DATASHEET_TFLOPS = 148 * 128 * 1.965e9 / 1e12  # 37.2: 148 SMs x 64 FMA/clk x 2 x 1.965 GHz
+SEED = 20200210
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="matrix order of the tensor elements")
+    ap.add_argument("--count", type=int, default=4096, help="tensor elements per GPU")
+    ap.add_argument("--e2e-count", type=int, default=0, help="tensor elements per GPU for the e2e leg (0 = --count)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-peaks", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--ref-sample", type=int, default=512, help="matrices per step for --impl reference")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        # "under load": samples at or above the median power draw
+        if sm:
+            cut = statistics.median(pw)
+            load = [s for s, p in zip(sm, pw) if p >= cut] or sm
+            return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                    "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+
+
+def run_peaks():
+    exe = os.path.join(ROOT, "tools", "bin", "peaks")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe, "--quick"], capture_output=True, text=True, timeout=240)
+        return json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else None
+    except Exception:
+        return None
+
+
+def cpu_baseline(n, seconds):
+    """OpenBLAS dgemm (numpy) on all host cores over a bounded sample of the workload."""
+    import numpy as np
+    from oracle import oracle_py as orc
+    cores = len(os.sched_getaffinity(0))
+    F = orc.fill_uniform(SEED, 0, (n, n))
+    sample = [orc.fill_uniform(SEED, i + 1, (n, n)) for i in range(16)]
+    orc.cpu_product(sample[0], F)  # warm up the thread pool
+    done, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for t in sample:
+            orc.cpu_product(t, F)
+        done += len(sample)
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "matrices/s", "cores": cores, "kind": "port",
+            "tflops": done * 2.0 * n ** 3 / dt / 1e12,
+            "sample": f"{done} products {n}x{n} * {n}x{n} in {dt:.1f} s, numpy/OpenBLAS dgemm on {cores} "
+                      f"host threads (Eigen is not installed in the image; oracle.cpu_product)"}
+
+
+def reference_arm(args, rank, world):
+    """The unmodified reference (cuBLAS, pageable copies, one stream) on a bounded sample."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import oracle_py as orc
+    n, cnt = args.n, args.ref_sample
+    line = {"impl": "reference", "metric": "tensor_stream_matrices_per_s", "unit": "matrices/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"tensor_stream_right: T_i({n}x{n}) * F({n}x{n}), FP64 col-major",
+                       "matrices_per_step": cnt, "kind": "right"}}
+    F = orc.fill_uniform(SEED, 0, (n, n))
+    ts = [orc.fill_uniform(SEED, i + 1, (n, n)) for i in range(cnt)]
+    use_ref = False
+    if orc.Reference.available():
+        try:
+            ref = orc.Reference()
+            use_ref = ref.count_available_gpus() > 0
+        except OSError:
+            use_ref = False
+    times = []
+    if use_ref:
+        for i in range(args.warmup + args.steps):
+            _, sec = ref.tensor_stream(0, F, ts)
+            if i >= args.warmup:
+                times.append(sec)
+        kind, cores = "reference", 1
+        sample = (f"{cnt} matrices per step through the unmodified reference loop (copy_to_gpu -> gemm "
+                  f"-> convert, README.md:62-66): cuBLAS {n}^3 DGEMM on the same B200, pageable host "
+                  f"memory, one host thread (rank 0 only: the reference has no multi-GPU path)")
+        bytes_in, bytes_out = cnt * n * n * 8, cnt * n * n * 8
+    else:
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            for t in ts[: max(16, cnt // 8)]:
+                orc.cpu_product(t, F)
+            sec = (time.perf_counter() - t0) * cnt / max(16, cnt // 8)
+            if i >= args.warmup:
+                times.append(sec)
+        kind, cores = "port", len(os.sched_getaffinity(0))
+        sample = "oracle port (numpy/OpenBLAS) -- oracle/_ref not runnable here"
+        bytes_in = bytes_out = 0
+    ms = 1e3 * sum(times) / len(times)
+    val = cnt / (ms * 1e-3)
+    line.update({"value": val, "ms_per_step": ms,
+                 "tflops": val * 2.0 * n ** 3 / 1e12,
+                 "cpu_baseline": {"value": val, "unit": "matrices/s", "cores": cores, "kind": kind, "sample": sample},
+                 "e2e": {"value": val, "unit": "matrices/s", "h2d_bytes_per_step": bytes_in,
+                         "d2h_bytes_per_step": bytes_out},
+                 "gpu_launches": 0})
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import eigencuda_b200 as ec
+    from eigencuda_b200 import shard
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n, count = args.n, args.count
+    elems = n * n
+    stream = torch.cuda.current_stream()
+    pipe = ec.CudaPipeline(local, stream=stream.cuda_stream)
+
+    # ---- peaks (rank 0 at N=1: measured on this very box, before the run) ----
+    peaks = None
+    if world == 1 and not args.no_peaks:
+        peaks = run_peaks()
+
+    # ---- data: generated on the device; fixed operand broadcast once (NCCL) ----
+    F = torch.empty(elems, dtype=torch.float64, device=dev)
+    if rank == 0:
+        pipe.fill_uniform(SEED, 0, F.data_ptr(), elems, 1)
+    else:
+        F.fill_(float("nan"))
+    shard.broadcast_fixed(F, src=0)
+    T = torch.empty(count * elems, dtype=torch.float64, device=dev)
+    R = torch.empty(count * elems, dtype=torch.float64, device=dev)
+    first_id = 1 + rank * count          # global tensor index of this rank's first element
+    pipe.fill_uniform(SEED, first_id, T.data_ptr(), elems, count)
+    torch.cuda.synchronize()
+
+    flops_per_matrix = 2.0 * n ** 3
+
+    def step_resident():
+        pipe.tensor_stream_device(ec.EC_STREAM_RIGHT, F.data_ptr(), n, n, T.data_ptr(), R.data_ptr(),
+                                  count, n, n)
+
+    # ---- value: resident in HBM ----
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = pipe.launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    torch.cuda.synchronize()
+    evs[0].record(stream)
+    for i in range(args.steps):
+        step_resident()
+        evs[i + 1].record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    launches = pipe.launch_count() - l0
+    total_ms = evs[0].elapsed_time(evs[-1])
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    value = world * count / (ms_per_step * 1e-3)
+    kernel_ms = sum(step_ms) / len(step_ms)          # one launch per step
+    achieved_tflops = count * flops_per_matrix / (kernel_ms * 1e-3) / 1e12
+
+    # sanity: a sampled result against the CPU oracle (outside every timed region)
+    if rank == 0:
+        from oracle import oracle_py as orc
+        i = count // 2
+        Ri = R[i * elems:(i + 1) * elems].cpu().numpy().reshape(n, n, order="F")
+        want = orc.cpu_product(orc.fill_uniform(SEED, first_id + i, (n, n)), orc.fill_uniform(SEED, 0, (n, n)))
+        err = orc.rel_frobenius(Ri, want)
+        if not err <= 1e-12:
+            raise SystemExit(f"bench.py: parity check failed, rel. Frobenius error {err}")
+    else:
+        err = None
+
+    # ---- e2e: through the C-ABI tensor-stream call with pinned host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        ecount = args.e2e_count or count
+        pin_in = pin_out = None
+        while ecount >= 64:
+            try:
+                pin_in = ec.PinnedBuffer((elems, ecount))
+                pin_out = ec.PinnedBuffer((elems, ecount))
+                break
+            except ec.EigenCudaError:
+                if pin_in is not None:
+                    pin_in.close()
+                pin_in = None
+                ecount //= 2
+        if pin_in is not None:
+            hin = torch.from_numpy(pin_in.array.reshape(-1, order="F"))
+            hin.copy_(T[: ecount * elems])          # inputs now live in pinned HOST memory
+            torch.cuda.synchronize()
+            in_ptrs = (C.c_void_p * ecount)(*[pin_in.ptr + 8 * elems * i for i in range(ecount)])
+            out_ptrs = (C.c_void_p * ecount)(*[pin_out.ptr + 8 * elems * i for i in range(ecount)])
+
+            def step_e2e():
+                pipe.tensor_stream_raw(ec.EC_STREAM_RIGHT, F.data_ptr(), n, n, in_ptrs, out_ptrs, ecount, n, n)
+
+            esteps = args.e2e_steps or min(args.steps, 5)
+            step_e2e()                                # warm-up (allocates the engine's ring)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(esteps):
+                step_e2e()                            # returns with all results in host memory
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            barrier()
+            dt = max_over_ranks(dt)
+            if rank == 0:
+                got = pin_out.array[:, ecount // 3].reshape(n, n, order="F")
+                want = orc.cpu_product(orc.fill_uniform(SEED, first_id + ecount // 3, (n, n)),
+                                       orc.fill_uniform(SEED, 0, (n, n)))
+                e_err = orc.rel_frobenius(got, want)
+                if not e_err <= 1e-12:
+                    raise SystemExit(f"bench.py: e2e parity check failed, rel. Frobenius error {e_err}")
+            e_val = world * ecount * esteps / dt
+            e2e = {"value": e_val, "unit": "matrices/s",
+                   "h2d_bytes_per_step": ecount * elems * 8, "d2h_bytes_per_step": ecount * elems * 8,
+                   "steps": esteps, "matrices_per_gpu": ecount, "ms_per_step": 1e3 * dt / esteps,
+                   "host_memory": "pinned (cudaHostAlloc), DMA'd in place",
+                   "tflops": e_val * flops_per_matrix / 1e12,
+                   "link_gbs_each_way_per_gpu": ecount * elems * 8 * esteps / dt / 1e9}
+            pin_in.close()
+            pin_out.close()
+
+    # ---- configs[1]: square DGEMM sweep on one GPU (rank 0, N=1) ----
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        sweep = []
+        del T, R
+        torch.cuda.empty_cache()
+        for nn in (1024, 2048, 4096, 8192):
+            A = torch.empty(nn * nn, dtype=torch.float64, device=dev)
+            B = torch.empty(nn * nn, dtype=torch.float64, device=dev)
+            Cm = torch.empty(nn * nn, dtype=torch.float64, device=dev)
+            pipe.fill_uniform(SEED, 0, A.data_ptr(), nn * nn, 1)
+            pipe.fill_uniform(SEED, 1, B.data_ptr(), nn * nn, 1)
+            reps = 3 if nn >= 8192 else 10
+            for _ in range(3):
+                pipe.dgemm(0, 0, nn, nn, nn, 1.0, A.data_ptr(), nn, B.data_ptr(), nn, 0.0, Cm.data_ptr(), nn)
+            best = float("inf")
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                pipe.dgemm(0, 0, nn, nn, nn, 1.0, A.data_ptr(), nn, B.data_ptr(), nn, 0.0, Cm.data_ptr(), nn)
+                b.record(stream)
+                b.synchronize()
+                best = min(best, a.elapsed_time(b))
+            tf = 2.0 * nn ** 3 / (best * 1e-3) / 1e12
+            sweep.append({"n": nn, "ms": best, "tflops": tf, "frac_of_datasheet_fp64": tf / FP64_DATASHEET_TFLOPS})
+            del A, B, Cm
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(n, args.cpu_seconds)
+
+    if rank == 0:
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "tensor", "achieved": achieved_tflops, "peak": FP64_DATASHEET_TFLOPS,
+                    "unit": "TFLOP/s", "frac": achieved_tflops / FP64_DATASHEET_TFLOPS, "traffic": traffic,
+                    "kernel": "dgemm_tma_dmma_kernel<NN> (FP64 DMMA, mma.sync.m8n8k4)",
+                    "kernel_ms": kernel_ms, "launches_per_step": launches / args.steps,
+                    "algorithmic_flops_per_launch": count * flops_per_matrix,
+                    "algorithmic_hbm_bytes_per_launch": count * 2 * elems * 8 + elems * 8,
+                    "hbm_gbs_achieved": (count * 2 * elems * 8 + elems * 8) / (kernel_ms * 1e-3) / 1e9,
+                    "peak_source": "datasheet-derived FP64 peak 148 SM x 128 flop/clk x 1.965 GHz "
+                                   "(MEASURED_PEAKS.json has no FP64 figure; of fallback/datasheet)"}
+        if peaks:
+            roofline["measured_dmma_issue_peak_tflops"] = peaks.get("dmma_peak_tflops")
+            roofline["measured_dmma_sustained_tflops"] = peaks.get("dmma_sustained_tflops")
+            if peaks.get("dmma_peak_tflops"):
+                roofline["frac_of_measured_dmma_peak"] = achieved_tflops / peaks["dmma_peak_tflops"]
+        line = {"metric": "tensor_stream_matrices_per_s", "value": value, "unit": "matrices/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"tensor_stream_right (BASELINE.json configs[2]): {count} matrices "
+                                       f"T_i({n}x{n}) per GPU, R_i = T_i * F({n}x{n}), FP64 column-major",
+                           "matrices_per_gpu": count, "n": n, "kind": "right",
+                           "parallelism": f"tensor sharded over {world} GPU(s), fixed operand broadcast once",
+                           "l2": f"inputs {count * elems * 8 / 2**30:.1f} GiB per step per GPU > 126 MB L2; no flush needed",
+                           "generator": "splitmix64 counter-based, seed 20200210"},
+                "tflops": value * flops_per_matrix / 1e12,
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu, "dgemm": sweep, "peaks": peaks,
+                "parity_rel_frobenius": err}
+        print(json.dumps(line), flush=True)
+    pipe.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,422 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle,
+against the committed golden vectors and -- when oracle/_ref is present -- against the unmodified
+reference (cuBLAS) on the same inputs.
+
+Bar (BASELINE.json north_star): relative Frobenius error <= 1e-12 for the native FP64 path (the
+reference's own tests use Eigen isApprox, whose default precision for double is 1e-12:
+/root/reference/src/tests/test_dot.cc:31,50,87-89).  Byte-moving paths (H2D/D2H round trips, the
+synthetic generator) must be bit-exact.  Full-size cases (BASELINE.json configs 2-4) are checked
+through size-independent properties: Freivalds products, identity, linearity, sampled elements.
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import eigencuda_b200 as ec
+from oracle import oracle_py as orc
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+TOL = 1e-12  # relative Frobenius, BASELINE.json north_star / Eigen isApprox default
+
+
+@pytest.fixture(scope="module")
+def pipe():
+    if ec.count_available_gpus() < 1:
+        pytest.fail("gpu tests need a B200; there is no CPU fallback")
+    p = ec.CudaPipeline(0)
+    yield p
+    p.close()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not orc.Reference.available():
+        pytest.skip("oracle/_ref not built (only built where /root/reference exists)")
+    return orc.Reference()
+
+
+def _mat(d):
+    return np.asfortranarray(np.array(d["row_major"], dtype=np.float64).reshape(d["rows"], d["cols"]))
+
+
+def rnd(seed, shape):
+    return np.asfortranarray(np.random.default_rng(seed).uniform(-1, 1, shape))
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own four test cases, through the mirrored API
+# ---------------------------------------------------------------------------------------------
+def test_create_cudamatrix_roundtrip(pipe):
+    """src/tests/test_dot.cc:11-32: H2D in the ctor, D2H in the conversion, bit-exact."""
+    g = json.load(open(os.path.join(GOLD, "readme_example.json")))
+    A, B, X = _mat(g["A"]), _mat(g["tensor"][0]), _mat(g["expected"][0])
+    cumatrix = ec.CudaMatrix(B, pipe.get_stream())
+    tmp = cumatrix.to_eigen()
+    assert np.array_equal(tmp, B)
+    assert tmp.ravel(order="K").tolist() == g["column_major_bytes"]["B"]
+    assert orc.is_approx(tmp @ A, X)
+    assert (cumatrix.rows(), cumatrix.cols(), cumatrix.size()) == (3, 2, 6)
+
+
+def test_matrix_multiplication_200(pipe, ref):
+    """src/tests/test_dot.cc:34-51: 200x200 random, vs the CPU product with isApprox."""
+    A, B = rnd(1, (200, 200)), rnd(2, (200, 200))
+    cA, cB = ec.CudaMatrix(A, pipe.get_stream()), ec.CudaMatrix(B, pipe.get_stream())
+    cC = ec.CudaMatrix(200, 200, pipe.get_stream())
+    pipe.gemm(cA, cB, cC)
+    got = cC.to_eigen()
+    assert orc.is_approx(got, orc.cpu_product(A, B))            # "Eigen's CPU product"
+    assert orc.rel_frobenius(got, orc.dgemm(A, B, flavour="ld")) <= TOL
+    assert orc.rel_frobenius(got, ref.gemm(A, B)) <= TOL        # the reference's cuBLAS path
+
+
+def test_right_matrix_multiplication_readme(pipe):
+    """src/tests/test_dot.cc:53-90 / README.md:37-72: the streaming pattern, known answers."""
+    g = json.load(open(os.path.join(GOLD, "readme_example.json")))
+    A = _mat(g["A"])
+    tensor = [_mat(t) for t in g["tensor"]]
+    want = [_mat(x) for x in g["expected"]]
+    cuma_A = ec.CudaMatrix(A, pipe.get_stream())
+    cuma_B = ec.CudaMatrix(3, 2, pipe.get_stream())
+    cuma_C = ec.CudaMatrix(3, 2, pipe.get_stream())
+    results = []
+    for i in range(3):
+        cuma_B.copy_to_gpu(tensor[i])
+        pipe.gemm(cuma_B, cuma_A, cuma_C)
+        results.append(cuma_C.to_eigen())
+    for r, x in zip(results, want):
+        assert np.array_equal(r, x)          # small integers: exact
+    # the same job as one overlapped call
+    for r, x in zip(pipe.right_multiply(tensor, A), want):
+        assert np.array_equal(r, x)
+
+
+def test_wrong_shape_raises_before_device_work(pipe):
+    """src/tests/test_dot.cc:92-103."""
+    cA = ec.CudaMatrix(rnd(3, (2, 2)), pipe.get_stream())
+    cB = ec.CudaMatrix(rnd(4, (5, 5)), pipe.get_stream())
+    cC = ec.CudaMatrix(2, 5, pipe.get_stream())
+    before = pipe.launch_count()
+    with pytest.raises(RuntimeError) as e:
+        pipe.gemm(cA, cB, cC)
+    assert e.value.code == 1 and "Shape mismatch" in str(e.value)
+    assert pipe.launch_count() == before
+    with pytest.raises(RuntimeError):
+        pipe.right_multiply([rnd(5, (3, 2))], rnd(6, (5, 5)))
+
+
+def test_cpp_compat_binary(tmp_path):
+    """Caller code written like the reference's tests, compiled against include/*.hpp, runs green."""
+    exe = tmp_path / "test_dot_compat"
+    cmd = ["g++", "-std=c++14", "-O2", f"-I{ROOT}/include", f"-I{ROOT}/oracle/eigen_standin",
+           "-I/usr/local/cuda/include", f"{ROOT}/tests/cpp/test_dot_compat.cc", "-o", str(exe),
+           f"-L{ROOT}/eigencuda_b200/lib", "-leigencuda_b200", f"-Wl,-rpath,{ROOT}/eigencuda_b200/lib"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "ALL PASSED" in res.stdout, res.stdout + res.stderr
+
+
+# ---------------------------------------------------------------------------------------------
+# golden fixture captured from the unmodified reference
+# ---------------------------------------------------------------------------------------------
+def test_against_committed_reference_outputs(pipe):
+    path = os.path.join(GOLD, "ref_cublas.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/ref_cublas.npz not generated yet")
+    from tests.golden.make_ref_golden import CASES, STREAM
+    z = np.load(path)
+    for cid, (name, m, k, n) in enumerate(CASES):
+        A = orc.fill_uniform(orc.SEED, 1000 + 2 * cid, (m, k))
+        B = orc.fill_uniform(orc.SEED, 1001 + 2 * cid, (k, n))
+        cA, cB = ec.CudaMatrix(A, pipe.get_stream()), ec.CudaMatrix(B, pipe.get_stream())
+        cC = ec.CudaMatrix(m, n, pipe.get_stream())
+        pipe.gemm(cA, cB, cC)
+        assert orc.rel_frobenius(cC.to_eigen(), z[name]) <= TOL, name
+    _, cnt, r, c = STREAM
+    F = orc.fill_uniform(orc.SEED, 0, (c, c))
+    ts = [orc.fill_uniform(orc.SEED, i + 1, (r, c)) for i in range(cnt)]
+    for got, want in zip(pipe.right_multiply(ts, F), z["stream_right"]):
+        assert orc.rel_frobenius(got, want) <= TOL
+    for got, want in zip(pipe.left_multiply(F, ts), z["stream_left"]):
+        assert orc.rel_frobenius(got, want) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# the DGEMM kernels: every op(A)/op(B), ragged shapes, leading dimensions, alpha/beta
+# ---------------------------------------------------------------------------------------------
+SHAPES = [  # (m, n, k)
+    (128, 128, 16), (128, 128, 128), (256, 384, 512), (130, 258, 70), (200, 200, 200),
+    (64, 64, 64), (520, 136, 1030), (32, 1024, 48), (1024, 40, 24), (40, 72, 96),
+]
+
+
+def run_dgemm(pipe, ta, tb, m, n, k, alpha, beta, lda_pad=0, ldb_pad=0, ldc_pad=0, seed=0):
+    a_shape = (k, m) if ta else (m, k)
+    b_shape = (n, k) if tb else (k, n)
+    Afull = rnd(seed + 1, (a_shape[0] + lda_pad, a_shape[1]))
+    Bfull = rnd(seed + 2, (b_shape[0] + ldb_pad, b_shape[1]))
+    Cfull = rnd(seed + 3, (m + ldc_pad, n))
+    dA, dB = ec.CudaMatrix(Afull, pipe.get_stream()), ec.CudaMatrix(Bfull, pipe.get_stream())
+    dC = ec.CudaMatrix(Cfull, pipe.get_stream())
+    pipe.dgemm(int(ta), int(tb), m, n, k, alpha, dA.data(), Afull.shape[0], dB.data(),
+               Bfull.shape[0], beta, dC.data(), Cfull.shape[0])
+    got_full = dC.to_eigen()
+    A, B = Afull[:a_shape[0]], Bfull[:b_shape[0]]
+    want = orc.dgemm(A, B, ta, tb, alpha, beta, Cin=Cfull[:m], flavour="ld")
+    # rows of C beyond m (the ldc padding) must be untouched
+    assert np.array_equal(got_full[m:], Cfull[m:])
+    return got_full[:m], want
+
+
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_dgemm_tma_kernel_all_layouts(pipe, ta, tb, shape):
+    m, n, k = shape
+    got, want = run_dgemm(pipe, ta, tb, m, n, k, 1.0, 0.0, seed=m + n + k)
+    assert pipe.last_kernel() == "tma_dmma_" + ("T" if ta else "N") + ("T" if tb else "N")
+    assert orc.rel_frobenius(got, want) <= TOL
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_dgemm_alpha_beta_and_padding(pipe, ta, tb):
+    got, want = run_dgemm(pipe, ta, tb, 200, 136, 88, -0.5, 2.25, lda_pad=6, ldb_pad=2, ldc_pad=4, seed=9)
+    assert pipe.last_kernel().startswith("tma_dmma")
+    assert orc.rel_frobenius(got, want) <= TOL
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("shape", [(3, 2, 2), (1, 1, 1), (7, 5, 3), (65, 33, 17), (129, 131, 67), (31, 200, 257)])
+def test_dgemm_simt_kernel_odd_shapes(pipe, ta, tb, shape):
+    """Odd leading dimensions cannot be TMA-addressed (16-byte pitch rule): generic kernel."""
+    m, n, k = shape
+    got, want = run_dgemm(pipe, ta, tb, m, n, k, 1.5, -0.75, lda_pad=0, ldb_pad=0, ldc_pad=1, seed=5)
+    if (k if ta else m) % 2 or (n if tb else k) % 2 or m * n * k < 64 ** 3:
+        assert pipe.last_kernel() == "simt"
+    assert orc.rel_frobenius(got, want) <= TOL
+
+
+def test_beta_zero_ignores_nan_in_c(pipe):
+    A, B = rnd(1, (160, 96)), rnd(2, (96, 144))
+    dA, dB = ec.CudaMatrix(A, pipe.get_stream()), ec.CudaMatrix(B, pipe.get_stream())
+    dC = ec.CudaMatrix(np.full((160, 144), np.nan, order="F"), pipe.get_stream())
+    pipe.gemm(dA, dB, dC)
+    got = dC.to_eigen()
+    assert np.isfinite(got).all()
+    assert orc.rel_frobenius(got, orc.dgemm(A, B, flavour="ld")) <= TOL
+
+
+def test_k_zero_and_alpha_zero_scale_c(pipe):
+    Cin = rnd(7, (40, 24))
+    dC = ec.CudaMatrix(Cin, pipe.get_stream())
+    dA = ec.CudaMatrix(rnd(8, (40, 8)), pipe.get_stream())
+    dB = ec.CudaMatrix(rnd(9, (8, 24)), pipe.get_stream())
+    pipe.dgemm(0, 0, 40, 24, 8, 0.0, dA.data(), 40, dB.data(), 8, 3.0, dC.data(), 40)
+    assert np.array_equal(dC.to_eigen(), 3.0 * Cin)
+    pipe.dgemm(0, 0, 40, 24, 0, 1.0, 0, 40, 0, 1, 0.0, dC.data(), 40)
+    assert np.array_equal(dC.to_eigen(), np.zeros((40, 24)))
+
+
+def test_empty_products_are_noops(pipe):
+    before = pipe.launch_count()
+    pipe.dgemm(0, 0, 0, 5, 3, 1.0, 0, 1, 0, 3, 0.0, 0, 1)
+    pipe.dgemm(0, 0, 5, 0, 3, 1.0, 0, 5, 0, 3, 0.0, 0, 5)
+    assert pipe.launch_count() == before
+    assert pipe.right_multiply([], np.eye(2)) == []
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True)])
+def test_strided_batched_matches_loop(pipe, ta, tb):
+    m, n, k, batch = 136, 72, 200, 5
+    a_shape = (k, m) if ta else (m, k)
+    b_shape = (n, k) if tb else (k, n)
+    As = np.asfortranarray(np.stack([rnd(i, a_shape) for i in range(batch)], axis=2))
+    Bf = rnd(99, b_shape)                      # shared operand: stride 0
+    dA = ec.CudaMatrix(As.reshape(a_shape[0], -1, order="F"), pipe.get_stream())
+    dB = ec.CudaMatrix(Bf, pipe.get_stream())
+    dC = ec.CudaMatrix(m, n * batch, pipe.get_stream())
+    pipe.dgemm_strided_batched(int(ta), int(tb), m, n, k, 1.0, dA.data(), a_shape[0],
+                               a_shape[0] * a_shape[1], dB.data(), b_shape[0], 0, 0.0, dC.data(), m,
+                               m * n, batch)
+    assert pipe.last_kernel().startswith("tma_dmma")
+    got = dC.to_eigen().reshape(m, n, batch, order="F")
+    for i in range(batch):
+        want = orc.dgemm(As[:, :, i], Bf, ta, tb, flavour="ld")
+        assert orc.rel_frobenius(got[:, :, i], want) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# memory subsystem: round trips are bit-exact, including the staged large-transfer paths
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1, 1), (3, 2), (1000, 1000), (1537, 911)])
+def test_upload_download_bit_exact(pipe, shape):
+    A = rnd(shape[0], shape)
+    dA = ec.CudaMatrix(A, pipe.get_stream())
+    assert np.array_equal(dA.to_eigen(), A)
+    B = rnd(shape[1] + 1, shape)
+    dA.copy_to_gpu(B)
+    B_copy = B.copy(order="F")
+    B[:] = 0.0                       # source is reusable as soon as copy_to_gpu returns
+    assert np.array_equal(dA.to_eigen(), B_copy)
+
+
+def test_copy_to_gpu_rejects_oversized_source(pipe):
+    d = ec.CudaMatrix(3, 2, pipe.get_stream())
+    with pytest.raises(RuntimeError):
+        d.copy_to_gpu(np.zeros((4, 2)))
+
+
+def test_out_of_memory_raises_runtime_error(pipe):
+    """src/cudamatrix.cc:63-79: a request beyond free device memory throws std::runtime_error."""
+    with pytest.raises(RuntimeError) as e:
+        ec.CudaMatrix(1 << 20, 1 << 20, pipe.get_stream())     # 8 TiB
+    assert e.value.code == 2 and "not enough memory" in str(e.value)
+
+
+def test_fill_uniform_matches_oracle_bit_for_bit(pipe):
+    n, batch = 1000, 3
+    d = ec.CudaMatrix(n, batch, pipe.get_stream())
+    pipe.fill_uniform(orc.SEED, 5, d.data(), n, batch)
+    got = d.to_eigen()
+    for b in range(batch):
+        assert np.array_equal(got[:, b], orc.fill_uniform(orc.SEED, 5 + b, (n,)))
+    gold = json.load(open(os.path.join(GOLD, "uniform_kat.json")))
+    e = gold["values"][0]
+    d1 = ec.CudaMatrix(1, 1, pipe.get_stream())
+    pipe.fill_uniform(gold["seed"], e["matrix_id"], d1.data(), 1, 1)
+    assert d1.to_eigen()[0, 0] == float.fromhex(e["hex"])
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor stream: every kind, pageable (staged) and pinned (direct DMA) host memory
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["right", "left", "left_t", "basis"])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_tensor_stream_kinds(pipe, kind, pinned):
+    n, count = 160, 23
+    F = orc.fill_uniform(orc.SEED, 0, (n, n))
+    bufs = []
+    if pinned:
+        pin = ec.PinnedBuffer((n, n, count))
+        pout = ec.PinnedBuffer((n, n, count))
+        bufs = [pin, pout]
+        ts = [pin.array[:, :, i] for i in range(count)]
+        for i, t in enumerate(ts):
+            t[:] = orc.fill_uniform(orc.SEED, i + 1, (n, n))
+        outs = [pout.array[:, :, i] for i in range(count)]
+    else:
+        ts = [orc.fill_uniform(orc.SEED, i + 1, (n, n)) for i in range(count)]
+        outs = None
+    pipe.set_stream_config(chunk_matrices=4, ring_depth=3, staging_threads=4)   # 6 chunks, ragged tail
+    code = {"right": ec.EC_STREAM_RIGHT, "left": ec.EC_STREAM_LEFT, "left_t": ec.EC_STREAM_LEFT_T,
+            "basis": ec.EC_STREAM_BASIS}[kind]
+    res = pipe.tensor_stream(code, F, ts, results=outs)
+    want = orc.tensor_stream(kind, F, ts, flavour="fast")
+    for r, w in zip(res, want):
+        assert orc.rel_frobenius(r, w) <= TOL
+    pipe.set_stream_config(0, 0, 0)
+    for b in bufs:
+        b.close()
+
+
+def test_tensor_stream_rectangular_reference_order(pipe, ref):
+    """T_i (r x c) * F (c x c2): the reference's gemm(cuma_B, cuma_A, cuma_C) order, vs the
+    unmodified reference run on the same inputs."""
+    r, c, c2, count = 96, 64, 48, 10
+    F = orc.fill_uniform(orc.SEED, 0, (c, c2))
+    ts = [orc.fill_uniform(orc.SEED, i + 1, (r, c)) for i in range(count)]
+    got = pipe.right_multiply(ts, F)
+    want, _ = ref.tensor_stream(0, F, ts)
+    for g, w in zip(got, want):
+        assert g.shape == (r, c2)
+        assert orc.rel_frobenius(g, w) <= TOL
+
+
+def test_tensor_stream_device_resident(pipe):
+    n, count = 128, 12
+    dF = ec.CudaMatrix(n, n, pipe.get_stream())
+    dT = ec.CudaMatrix(n, n * count, pipe.get_stream())
+    dR = ec.CudaMatrix(n, n * count, pipe.get_stream())
+    pipe.fill_uniform(orc.SEED, 0, dF.data(), n * n, 1)
+    pipe.fill_uniform(orc.SEED, 1, dT.data(), n * n, count)
+    for kind, name in [(ec.EC_STREAM_RIGHT, "right"), (ec.EC_STREAM_BASIS, "basis")]:
+        pipe.tensor_stream_device(kind, dF.data(), n, n, dT.data(), dR.data(), count, n, n)
+        got = dR.to_eigen().reshape(n, n, count, order="F")
+        F = orc.fill_uniform(orc.SEED, 0, (n, n))
+        ts = [orc.fill_uniform(orc.SEED, i + 1, (n, n)) for i in range(count)]
+        for i, w in enumerate(orc.tensor_stream(name, F, ts, flavour="fast")):
+            assert orc.rel_frobenius(got[:, :, i], w) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full sizes, through size-independent properties
+# ---------------------------------------------------------------------------------------------
+def test_full_size_square_8192_freivalds(pipe):
+    """config 2 at n = 8192: C x == A (B x) for random x (O(n^2) check of an O(n^3) product)."""
+    n = 8192
+    dA, dB = ec.CudaMatrix(n, n, pipe.get_stream()), ec.CudaMatrix(n, n, pipe.get_stream())
+    dC = ec.CudaMatrix(n, n, pipe.get_stream())
+    pipe.fill_uniform(orc.SEED, 0, dA.data(), n * n, 1)
+    pipe.fill_uniform(orc.SEED, 1, dB.data(), n * n, 1)
+    pipe.gemm(dA, dB, dC)
+    assert pipe.last_kernel() == "tma_dmma_NN"
+    A, B, Cm = dA.to_eigen(), dB.to_eigen(), dC.to_eigen()
+    assert np.array_equal(A[:5, 0], orc.fill_uniform(orc.SEED, 0, (5,)))
+    x = np.random.default_rng(0).uniform(-1, 1, (n, 4))
+    lhs, rhs = Cm @ x, A @ (B @ x)
+    assert np.linalg.norm(lhs - rhs) / np.linalg.norm(rhs) <= TOL
+    # sampled elements against long-double dot products
+    rng = np.random.default_rng(1)
+    for i, j in zip(rng.integers(0, n, 16), rng.integers(0, n, 16)):
+        want = float(np.dot(A[i, :].astype(np.longdouble), B[:, j].astype(np.longdouble)))
+        assert abs(Cm[i, j] - want) <= 1e-12 * np.linalg.norm(A[i, :]) * np.linalg.norm(B[:, j])
+
+
+def test_full_size_tensor_stream_4096x512(pipe):
+    """config 3: 4096 x (512x512) against a fixed 512x512, resident in HBM; identity, linearity
+    and sampled matrices against the oracle."""
+    n, count = 512, 4096
+    dF = ec.CudaMatrix(n, n, pipe.get_stream())
+    dT = ec.CudaMatrix(n, n * count, pipe.get_stream())
+    dR = ec.CudaMatrix(n, n * count, pipe.get_stream())
+    pipe.fill_uniform(orc.SEED, 0, dF.data(), n * n, 1)
+    pipe.fill_uniform(orc.SEED, 1, dT.data(), n * n, count)
+    pipe.tensor_stream_device(ec.EC_STREAM_RIGHT, dF.data(), n, n, dT.data(), dR.data(), count, n, n)
+    F = orc.fill_uniform(orc.SEED, 0, (n, n))
+    one = ec.CudaMatrix(n, n, pipe.get_stream())
+    dI = ec.CudaMatrix(np.eye(n, order="F"), pipe.get_stream())
+
+    def pull(i):
+        # result i out of the resident tensor through an identity product (itself a property:
+        # R_i * I == R_i exactly), without downloading the whole 8 GiB tensor
+        pipe.dgemm(0, 0, n, n, n, 1.0, dR.data() + 8 * n * n * i, n, dI.data(), n, 0.0, one.data(), n)
+        return one.to_eigen()
+
+    for i in (0, 1, 2047, 4095):
+        Ti = orc.fill_uniform(orc.SEED, i + 1, (n, n))
+        assert orc.rel_frobenius(pull(i), orc.cpu_product(Ti, F)) <= TOL
+    # linearity across the tensor: (T_0 + T_1) F == R_0 + R_1
+    R0, R1 = pull(0), pull(1)
+    T01 = orc.fill_uniform(orc.SEED, 1, (n, n)) + orc.fill_uniform(orc.SEED, 2, (n, n))
+    d01 = ec.CudaMatrix(T01, pipe.get_stream())
+    pipe.gemm(d01, dF, one)
+    assert orc.rel_frobenius(one.to_eigen(), R0 + R1) <= 4 * TOL
+
+
+def test_full_size_transposed_1000(pipe):
+    """config 4: A^T B and A^T M A at 1000 x 1000 (a few tensor elements), vs the oracle."""
+    n, count = 1000, 3
+    F = orc.fill_uniform(orc.SEED, 0, (n, n))
+    ts = [orc.fill_uniform(orc.SEED, i + 1, (n, n)) for i in range(count)]
+    for got, t in zip(pipe.left_multiply(F, ts, transpose=True), ts):
+        assert orc.rel_frobenius(got, orc.cpu_product(F.T, t)) <= TOL
+    for got, t in zip(pipe.basis_transform(F, ts), ts):
+        assert orc.rel_frobenius(got, orc.cpu_product(orc.cpu_product(F.T, t), F)) <= TOL
