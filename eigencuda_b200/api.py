@@ -95,6 +95,8 @@ class CudaMatrix:
 def _stream_arg(stream):
     if isinstance(stream, CudaPipeline):
         return stream.get_stream()
+    if isinstance(stream, C.c_void_p):
+        return stream
     return C.c_void_p(int(stream) if stream else 0)
 
 
