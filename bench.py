@@ -394,7 +394,9 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("bytes_per_launch")
+                # ncu --set full capture of one launch of the same kernel (profiles/): DRAM bytes
+                # per matrix there x the matrices this launch processes
+                traffic = json.load(open(tpath))["bytes_per_matrix"] * count
             except Exception:
                 traffic = None
         roofline = {"bound": "tensor", "achieved": achieved_tflops, "peak": FP64_DATASHEET_TFLOPS,
