@@ -27,22 +27,45 @@
 namespace ec {
 
 // ------------------------------------------------------------------------------------------
-// Tile configuration of the hot kernel
+// Tile configurations of the hot kernel
 // ------------------------------------------------------------------------------------------
-constexpr int BM = 128;            // C tile rows per CTA
-constexpr int BN = 128;            // C tile cols per CTA
-constexpr int BK = 16;             // k extent per stage: 16 doubles = 128 B = one swizzle span
-constexpr int STAGES = 5;          // 5 x 32 KiB ring
-constexpr int CONSUMER_WARPS = 8;  // 2 (m) x 4 (n), warp tile 64 x 32
-constexpr int WM = 64, WN = 32;
-// Three warpgroups: two of consumers, one whose first warp is the producer.  The register file
-// is allocated in 4-warp units anyway (9 warps cost the same as 12: 168 regs/thread), so the
-// producer group gives its registers away with setmaxnreg and the consumers grow to 232.
-constexpr int GEMM_THREADS = (CONSUMER_WARPS + 4) * 32;
-constexpr int PRODUCER_REGS = 40, CONSUMER_REGS = 232;
-constexpr int OPERAND_STAGE_BYTES = BM * BK * 8;             // 16 KiB (BM == BN)
-constexpr int STAGE_BYTES = 2 * OPERAND_STAGE_BYTES;         // 32 KiB
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int BK = 16;  // k extent per stage: 16 doubles = 128 B = one swizzle span
+
+// One CTA computes a BM x BN tile of C with (BM/WM) x (BN/WN) consumer warps, each holding a
+// WM x WN sub-tile in registers, plus one producer warpgroup (its first warp's elected lane issues
+// the TMA loads).  The register file is allocated per 4 warps, so a lone producer warp would cost
+// as much as four: the producer group hands its registers to the consumers with setmaxnreg.
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MIN_CTAS_>
+struct TileCfg {
+  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_;
+  static constexpr int MIN_CTAS = MIN_CTAS_;
+  static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+  static constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N;
+  static constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;
+  static constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN * BK * 8;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  // setmaxnreg moves registers inside the CTA's own launch allocation (THREADS x LAUNCH_REGS,
+  // LAUNCH_REGS = what __launch_bounds__(THREADS, MIN_CTAS) makes ptxas allocate); asking for more
+  // than that pool holds blocks forever, so the consumer budget is derived from it:
+  //   CONSUMER_WARPS*32*CONSUMER_REGS + 128*PRODUCER_REGS <= THREADS*LAUNCH_REGS
+  static constexpr int LAUNCH_REGS_RAW = (65536 / (MIN_CTAS * THREADS)) / 8 * 8;
+  static constexpr int LAUNCH_REGS = LAUNCH_REGS_RAW > 248 ? 248 : LAUNCH_REGS_RAW;
+  static constexpr int PRODUCER_REGS = MIN_CTAS == 1 ? 40 : 24;
+  static constexpr int CONSUMER_REGS_RAW =
+      ((THREADS * LAUNCH_REGS - 128 * PRODUCER_REGS) / (CONSUMER_WARPS * 32)) / 8 * 8;
+  static constexpr int CONSUMER_REGS = CONSUMER_REGS_RAW > 232 ? 232 : CONSUMER_REGS_RAW;
+  static_assert(CONSUMER_WARPS * 32 * CONSUMER_REGS + 128 * PRODUCER_REGS <= THREADS * LAUNCH_REGS,
+                "register split exceeds the CTA's launch allocation (setmaxnreg.inc would hang)");
+  static_assert(CONSUMER_REGS >= LAUNCH_REGS && PRODUCER_REGS <= LAUNCH_REGS, "inc/dec direction");
+  static_assert(WM % 16 == 0 && WN % 16 == 0 && BM % WM == 0 && BN % WN == 0, "tile shape");
+  static_assert(CONSUMER_WARPS % 4 == 0, "setmaxnreg works on whole warpgroups");
+};
+//                    BM   BN   WM  WN  ST  CTAs/SM
+using CfgL  = TileCfg<128, 128, 64, 32, 5, 1>;   // 8 consumer warps, 160 KiB, 232 regs
+using CfgM  = TileCfg<128,  64, 64, 32, 4, 2>;   // 4 consumer warps,  96 KiB, 232 regs
+using CfgS  = TileCfg< 64,  64, 32, 32, 4, 3>;   // 4 consumer warps,  64 KiB, 136 regs
+using CfgXS = TileCfg< 64,  32, 32, 16, 4, 4>;   // 4 consumer warps,  48 KiB, 104 regs
 
 struct GemmParams {
   int64_t M, N, K;
@@ -181,25 +204,28 @@ __device__ __forceinline__ void load_frags(uint32_t base, int w0, int kk, int g,
   }
 }
 
-// Producer side: fill one operand's stage.  K-major: one box; MN-major: eight boxes.
-template <bool KMAJOR>
+// Producer side: fill one operand's stage (EXTENT = BM or BN rows of the operand tile).
+// K-major: one box {16 k, EXTENT mn}; MN-major: EXTENT/16 boxes {16 mn, 16 k}.
+template <bool KMAJOR, int EXTENT>
 __device__ __forceinline__ void tma_fill_operand(uint32_t dst, const CUtensorMap *map, uint32_t bar,
                                                  int mn0, int k0, int b) {
   if (KMAJOR) {
     tma_load_3d(dst, map, bar, k0, mn0, b);
   } else {
 #pragma unroll
-    for (int j = 0; j < BM / 16; ++j) tma_load_3d(dst + j * 2048, map, bar, mn0 + 16 * j, k0, b);
+    for (int j = 0; j < EXTENT / 16; ++j) tma_load_3d(dst + j * 2048, map, bar, mn0 + 16 * j, k0, b);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // The hot kernel
 // ------------------------------------------------------------------------------------------
-template <bool A_KMAJOR, bool B_KMAJOR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <class Cfg, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
     dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap tmA,
                           const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
+  constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled TMA destinations need 1024-byte alignment.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -229,8 +255,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int tiles_per_problem = p.tiles_m * p.tiles_n;
 
   if (warp >= CONSUMER_WARPS) {
-    // ===================== TMA producer (one elected lane of the third warpgroup) ===========
-    setmaxnreg_dec<PRODUCER_REGS>();
+    // ===================== TMA producer (one elected lane) =====================
+    setmaxnreg_dec<Cfg::PRODUCER_REGS>();
     if (warp == CONSUMER_WARPS && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -244,9 +270,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           const uint32_t sA = smem_base + stage * STAGE_BYTES;
-          const uint32_t sB = sA + OPERAND_STAGE_BYTES;
-          tma_fill_operand<A_KMAJOR>(sA, &tmA, full_bar(stage), m0, kb * BK, ba);
-          tma_fill_operand<B_KMAJOR>(sB, &tmB, full_bar(stage), n0, kb * BK, bb);
+          const uint32_t sB = sA + Cfg::A_BYTES;
+          tma_fill_operand<A_KMAJOR, BM>(sA, &tmA, full_bar(stage), m0, kb * BK, ba);
+          tma_fill_operand<B_KMAJOR, BN>(sB, &tmB, full_bar(stage), n0, kb * BK, bb);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -258,12 +284,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   }
 
   // ===================== DMMA consumers =====================
-  setmaxnreg_inc<CONSUMER_REGS>();
+  setmaxnreg_inc<Cfg::CONSUMER_REGS>();
   const int g = lane >> 2, c = lane & 3;
-  const int wm0 = (warp & 1) * WM;   // warp's row offset inside the CTA tile
-  const int wn0 = (warp >> 1) * WN;  // warp's column offset
-  constexpr int MB = WM / 8;         // 8 row blocks
-  constexpr int NB = WN / 8;         // 4 column blocks
+  const int wm0 = (warp % Cfg::WARPS_M) * WM;  // warp's row offset inside the CTA tile
+  const int wn0 = (warp / Cfg::WARPS_M) * WN;  // warp's column offset
+  constexpr int MB = WM / 8;                   // row blocks per warp
+  constexpr int NB = WN / 8;                   // column blocks per warp
 
   int stage = 0;
   uint32_t phase = 0;
@@ -282,7 +308,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     for (int kb = 0; kb < kblocks; ++kb) {
       mbar_wait(full_bar(stage), phase);
       const uint32_t sA = smem_base + stage * STAGE_BYTES;
-      const uint32_t sB = sA + OPERAND_STAGE_BYTES;
+      const uint32_t sB = sA + Cfg::A_BYTES;
 #pragma unroll
       for (int kk = 0; kk < BK; kk += 8) {
         double ae[MB], ao[MB], be[NB], bo[NB];

@@ -271,7 +271,7 @@ bool tma_ok(const Operand &o, int64_t batch) {
   return true;
 }
 
-int make_tensor_map(CUtensorMap *tm, const Operand &o, int64_t batch) {
+int make_tensor_map(CUtensorMap *tm, const Operand &o, int64_t batch, int tile_extent) {
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) return fail(EC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   const bool batched = batch > 1 && o.stride != 0;
@@ -285,7 +285,7 @@ int make_tensor_map(CUtensorMap *tm, const Operand &o, int64_t batch) {
   // stride of the (possibly degenerate) batch dimension: any legal multiple of 16 when unused
   strides[1] = batched ? (cuuint64_t)o.stride * 8 : (cuuint64_t)o.ld * 8 * (cuuint64_t)std::max<int64_t>(outer, 1);
   box[0] = 16;
-  box[1] = o.kmajor ? (cuuint32_t)ec::BM : (cuuint32_t)ec::BK;
+  box[1] = o.kmajor ? (cuuint32_t)tile_extent : (cuuint32_t)ec::BK;
   box[2] = 1;
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)o.ptr, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -295,22 +295,81 @@ int make_tensor_map(CUtensorMap *tm, const Operand &o, int64_t batch) {
   return EC_OK;
 }
 
-template <bool AK, bool BK_>
+template <class Cfg, bool AK, bool BK_>
 int launch_tma_dmma(ec_pipeline *p, const CUtensorMap &tmA, const CUtensorMap &tmB,
                     const ec::GemmParams &gp) {
-  auto kern = ec::dgemm_tma_dmma_kernel<AK, BK_>;
+  auto kern = ec::dgemm_tma_dmma_kernel<Cfg, AK, BK_>;
   static std::atomic<uint64_t> configured{0};  // per instantiation, one bit per device
   const uint64_t bit = 1ull << (p->device & 63);
   if (!(configured.load() & bit)) {
     EC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 ec::GEMM_SMEM_BYTES));
+                                 Cfg::SMEM_BYTES));
     configured.fetch_or(bit);
   }
-  const int grid = (int)std::min<int64_t>(gp.total_tiles, p->sm_count);
-  kern<<<grid, ec::GEMM_THREADS, ec::GEMM_SMEM_BYTES, p->stream>>>(tmA, tmB, gp);
+  const int grid = (int)std::min<int64_t>(gp.total_tiles, (int64_t)p->sm_count * Cfg::MIN_CTAS);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, p->stream>>>(tmA, tmB, gp);
   EC_CUDA(cudaGetLastError());
   p->launches++;
   return EC_OK;
+}
+
+template <class Cfg>
+int run_tma_dmma(ec_pipeline *p, const Operand &oa, const Operand &ob, int64_t m, int64_t n,
+                 int64_t k, double alpha, double beta, double *C, int64_t ldc, int64_t stride_c,
+                 int64_t stride_a, int64_t stride_b, int64_t batch, const char *const names[4]) {
+  CUtensorMap tmA, tmB;
+  int rc = make_tensor_map(&tmA, oa, batch, Cfg::BM);
+  if (rc) return rc;
+  rc = make_tensor_map(&tmB, ob, batch, Cfg::BN);
+  if (rc) return rc;
+  ec::GemmParams gp;
+  gp.M = m; gp.N = n; gp.K = k; gp.batch = batch;
+  gp.alpha = alpha; gp.beta = beta;
+  gp.C = C; gp.ldc = ldc; gp.stride_c = stride_c;
+  gp.tiles_m = (int)((m + Cfg::BM - 1) / Cfg::BM);
+  gp.tiles_n = (int)((n + Cfg::BN - 1) / Cfg::BN);
+  gp.total_tiles = (int64_t)gp.tiles_m * gp.tiles_n * batch;
+  gp.a_batched = (batch > 1 && stride_a != 0);
+  gp.b_batched = (batch > 1 && stride_b != 0);
+  if (oa.kmajor && ob.kmajor) { p->last_kernel = names[0]; return launch_tma_dmma<Cfg, true, true>(p, tmA, tmB, gp); }
+  if (oa.kmajor && !ob.kmajor) { p->last_kernel = names[1]; return launch_tma_dmma<Cfg, true, false>(p, tmA, tmB, gp); }
+  if (!oa.kmajor && ob.kmajor) { p->last_kernel = names[2]; return launch_tma_dmma<Cfg, false, true>(p, tmA, tmB, gp); }
+  p->last_kernel = names[3];
+  return launch_tma_dmma<Cfg, false, false>(p, tmA, tmB, gp);
+}
+
+// Tile choice.  All configurations run the DMMA pipe at the same rate once it is fed; what
+// differs is (a) load balance -- the per-SM pipe time is ceil(tiles / SMs) tiles' worth, so
+// finer tiles waste less on the last wave -- and (b) per-tile overhead (prologue/epilogue), which
+// configurations with >= 2 CTAs per SM hide behind the other CTA's main loop.  Cost model in SM
+// clocks; the constants come from the tile sweep in profiles/ (tools/tile_sweep.py).
+enum { TILE_AUTO = 0, TILE_L = 1, TILE_M = 2, TILE_S = 3, TILE_XS = 4 };
+
+int choose_tile(const ec_pipeline *p, int64_t m, int64_t n, int64_t k, int64_t batch) {
+  // EC_FORCE_TILE=1..4 overrides the choice (tools/tile_sweep.py); read per call, it is cheap
+  if (const char *e = getenv("EC_FORCE_TILE")) {
+    const int f = atoi(e);
+    if (f >= TILE_L && f <= TILE_XS) return f;
+  }
+  struct Cand { int id, bm, bn, ctas; double eff, overhead; };
+  // eff: fraction of the DMMA issue rate the main loop sustains; overhead: exposed clocks per tile
+  // fitted to profiles/r01_tile_sweep.json (B200): L sustains 98.7 % of the issue rate in the
+  // main loop with ~3.3k exposed clocks per tile; the finer tiles trade main-loop efficiency
+  // (more LDS per DMMA) for balance; two CTAs per SM run in lockstep and hide less than hoped
+  const Cand cands[4] = {{TILE_L, 128, 128, 1, 0.987, 3300.0},
+                         {TILE_M, 128, 64, 2, 0.985, 2600.0},
+                         {TILE_S, 64, 64, 3, 0.955, 1500.0},
+                         {TILE_XS, 64, 32, 4, 0.93, 1000.0}};
+  double best = 1e300;
+  int pick = TILE_M;
+  for (const Cand &c : cands) {
+    const int64_t tiles = ((m + c.bm - 1) / c.bm) * ((n + c.bn - 1) / c.bn) * batch;
+    const int64_t per_sm = (tiles + p->sm_count - 1) / p->sm_count;   // tiles on the busiest SM
+    const double tile_clk = (double)c.bm * c.bn * (double)((k + 15) / 16 * 16) / 64.0 / c.eff + c.overhead;
+    const double cost = per_sm * tile_clk;
+    if (cost < best) { best = cost; pick = c.id; }
+  }
+  return pick;
 }
 
 int dgemm_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n, int64_t k,
@@ -343,30 +402,21 @@ int dgemm_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
 
   Operand oa{A, lda, stride_a, transa == EC_OP_T, m, k};
   Operand ob{B, ldb, stride_b, transb == EC_OP_N, n, k};
-  // Tiny problems are latency-bound whichever kernel runs; the 128x128 persistent tile only
-  // pays off once a problem has at least a tile's worth of rows, columns and depth.
+  // Tiny problems are latency-bound whichever kernel runs; the TMA pipeline only pays off once a
+  // problem has at least a small tile's worth of rows, columns and depth.
   const bool big_enough = (m >= 32 && n >= 32 && k >= 16) && (m * n * k >= (int64_t)64 * 64 * 64);
   const bool c_ok = m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31);
   if (big_enough && c_ok && tma_ok(oa, batch) && tma_ok(ob, batch)) {
-    CUtensorMap tmA, tmB;
-    int rc = make_tensor_map(&tmA, oa, batch);
-    if (rc) return rc;
-    rc = make_tensor_map(&tmB, ob, batch);
-    if (rc) return rc;
-    ec::GemmParams gp;
-    gp.M = m; gp.N = n; gp.K = k; gp.batch = batch;
-    gp.alpha = alpha; gp.beta = beta;
-    gp.C = C; gp.ldc = ldc; gp.stride_c = stride_c;
-    gp.tiles_m = (int)((m + ec::BM - 1) / ec::BM);
-    gp.tiles_n = (int)((n + ec::BN - 1) / ec::BN);
-    gp.total_tiles = (int64_t)gp.tiles_m * gp.tiles_n * batch;
-    gp.a_batched = (batch > 1 && stride_a != 0);
-    gp.b_batched = (batch > 1 && stride_b != 0);
-    if (oa.kmajor && ob.kmajor) { p->last_kernel = "tma_dmma_TN"; return launch_tma_dmma<true, true>(p, tmA, tmB, gp); }
-    if (oa.kmajor && !ob.kmajor) { p->last_kernel = "tma_dmma_TT"; return launch_tma_dmma<true, false>(p, tmA, tmB, gp); }
-    if (!oa.kmajor && ob.kmajor) { p->last_kernel = "tma_dmma_NN"; return launch_tma_dmma<false, true>(p, tmA, tmB, gp); }
-    p->last_kernel = "tma_dmma_NT";
-    return launch_tma_dmma<false, false>(p, tmA, tmB, gp);
+    static const char *const nL[4] = {"tma_dmma_TN", "tma_dmma_TT", "tma_dmma_NN", "tma_dmma_NT"};
+    static const char *const nM[4] = {"tma_dmma_TN_m", "tma_dmma_TT_m", "tma_dmma_NN_m", "tma_dmma_NT_m"};
+    static const char *const nS[4] = {"tma_dmma_TN_s", "tma_dmma_TT_s", "tma_dmma_NN_s", "tma_dmma_NT_s"};
+    static const char *const nX[4] = {"tma_dmma_TN_xs", "tma_dmma_TT_xs", "tma_dmma_NN_xs", "tma_dmma_NT_xs"};
+    switch (choose_tile(p, m, n, k, batch)) {
+      case TILE_L: return run_tma_dmma<ec::CfgL>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, nL);
+      case TILE_S: return run_tma_dmma<ec::CfgS>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, nS);
+      case TILE_XS: return run_tma_dmma<ec::CfgXS>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, nX);
+      default: return run_tma_dmma<ec::CfgM>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, nM);
+    }
   }
 
   ec::SimtParams sp;
