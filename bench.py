@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--no-peaks", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-sample", type=int, default=512, help="matrices per step for --impl reference")
+    ap.add_argument("--chunk", type=int, default=0, help="tensor-stream engine: matrices per device chunk (0 = default)")
+    ap.add_argument("--ring", type=int, default=0, help="tensor-stream engine: ring depth (0 = default)")
     return ap.parse_args()
 
 
@@ -330,6 +332,7 @@ def main():
             def step_e2e():
                 pipe.tensor_stream_raw(ec.EC_STREAM_RIGHT, F.data_ptr(), n, n, in_ptrs, out_ptrs, ecount, n, n)
 
+            pipe.set_stream_config(args.chunk, args.ring, 0)
             esteps = args.e2e_steps or min(args.steps, 5)
             step_e2e()                                # warm-up (allocates the engine's ring)
             torch.cuda.synchronize()

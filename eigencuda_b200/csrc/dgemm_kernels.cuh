@@ -35,19 +35,20 @@ constexpr int BK = 16;  // k extent per stage: 16 doubles = 128 B = one swizzle 
 // WM x WN sub-tile in registers, plus one producer warpgroup (its first warp's elected lane issues
 // the TMA loads).  The register file is allocated per 4 warps, so a lone producer warp would cost
 // as much as four: the producer group hands its registers to the consumers with setmaxnreg.
-template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MIN_CTAS_>
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MIN_CTAS_, bool REGSPLIT_>
 struct TileCfg {
   static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_;
   static constexpr int MIN_CTAS = MIN_CTAS_;
+  static constexpr bool REGSPLIT = REGSPLIT_;
   static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
   static constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N;
-  static constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;
+  static constexpr int THREADS = (CONSUMER_WARPS + (REGSPLIT ? 4 : 1)) * 32;
   static constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN * BK * 8;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-  // setmaxnreg moves registers inside the CTA's own launch allocation (THREADS x LAUNCH_REGS,
-  // LAUNCH_REGS = what __launch_bounds__(THREADS, MIN_CTAS) makes ptxas allocate); asking for more
-  // than that pool holds blocks forever, so the consumer budget is derived from it:
+  // REGSPLIT: setmaxnreg moves registers inside the CTA's own launch allocation (THREADS x
+  // LAUNCH_REGS, LAUNCH_REGS = what __launch_bounds__(THREADS, MIN_CTAS) makes ptxas allocate);
+  // asking for more than that pool holds blocks forever, so the consumer budget is derived from it:
   //   CONSUMER_WARPS*32*CONSUMER_REGS + 128*PRODUCER_REGS <= THREADS*LAUNCH_REGS
   static constexpr int LAUNCH_REGS_RAW = (65536 / (MIN_CTAS * THREADS)) / 8 * 8;
   static constexpr int LAUNCH_REGS = LAUNCH_REGS_RAW > 248 ? 248 : LAUNCH_REGS_RAW;
@@ -55,17 +56,19 @@ struct TileCfg {
   static constexpr int CONSUMER_REGS_RAW =
       ((THREADS * LAUNCH_REGS - 128 * PRODUCER_REGS) / (CONSUMER_WARPS * 32)) / 8 * 8;
   static constexpr int CONSUMER_REGS = CONSUMER_REGS_RAW > 232 ? 232 : CONSUMER_REGS_RAW;
-  static_assert(CONSUMER_WARPS * 32 * CONSUMER_REGS + 128 * PRODUCER_REGS <= THREADS * LAUNCH_REGS,
+  static_assert(!REGSPLIT ||
+                    CONSUMER_WARPS * 32 * CONSUMER_REGS + 128 * PRODUCER_REGS <= THREADS * LAUNCH_REGS,
                 "register split exceeds the CTA's launch allocation (setmaxnreg.inc would hang)");
-  static_assert(CONSUMER_REGS >= LAUNCH_REGS && PRODUCER_REGS <= LAUNCH_REGS, "inc/dec direction");
+  static_assert(!REGSPLIT || (CONSUMER_REGS >= LAUNCH_REGS && PRODUCER_REGS <= LAUNCH_REGS), "inc/dec direction");
   static_assert(WM % 16 == 0 && WN % 16 == 0 && BM % WM == 0 && BN % WN == 0, "tile shape");
-  static_assert(CONSUMER_WARPS % 4 == 0, "setmaxnreg works on whole warpgroups");
+  static_assert(!REGSPLIT || CONSUMER_WARPS % 4 == 0, "setmaxnreg works on whole warpgroups");
 };
-//                    BM   BN   WM  WN  ST  CTAs/SM
-using CfgL  = TileCfg<128, 128, 64, 32, 5, 1>;   // 8 consumer warps, 160 KiB, 232 regs
-using CfgM  = TileCfg<128,  64, 64, 32, 4, 2>;   // 4 consumer warps,  96 KiB, 232 regs
-using CfgS  = TileCfg< 64,  64, 32, 32, 4, 3>;   // 4 consumer warps,  64 KiB, 136 regs
-using CfgXS = TileCfg< 64,  32, 32, 16, 4, 4>;   // 4 consumer warps,  48 KiB, 104 regs
+//                    BM   BN   WM  WN  ST CTAs regsplit
+using CfgL  = TileCfg<128, 128, 64, 32, 5, 1, true>;    // 8 consumer warps, 160 KiB, 232 regs
+using CfgS  = TileCfg< 64,  64, 32, 32, 4, 2, false>;   // 4 consumer warps,  64 KiB, 2 CTAs/SM
+using CfgXS = TileCfg< 64,  32, 32, 16, 4, 3, false>;   // 4 consumer warps,  48 KiB, 3 CTAs/SM
+// (A 128x64 / 2 CTAs-per-SM variant and register-split variants of the small tiles were measured
+//  and lost everywhere -- profiles/r01_tile_sweep*.json -- so they are not built.)
 
 struct GemmParams {
   int64_t M, N, K;
@@ -76,6 +79,16 @@ struct GemmParams {
   int tiles_m, tiles_n;
   int64_t total_tiles;
   int a_batched, b_batched;  // 0: operand shared by every problem of the batch (coordinate 0)
+  // Stream-K region (see "work schedule" below): tiles [0, sk_tiles) are cut along k into
+  // gridDim.x equal contiguous runs of k-iterations; tiles [sk_tiles, total_tiles) are whole
+  // tiles dealt round-robin.  sk_tiles == 0 -> plain data-parallel schedule.
+  int64_t sk_tiles;
+  double *sk_workspace;    // gridDim.x partial accumulator tiles, thread-linear layout
+  unsigned *sk_flags;      // gridDim.x flags; flag[c] == sk_epoch <=> CTA c's partial is published
+  unsigned sk_epoch;       // unique per launch, so flags never need resetting
+  int c_vec2;              // C base, ldc and batch stride are 16-byte aligned: row pairs may use 16 B stores
+  int sk_sms;              // SM count: CTAs b and b + sk_sms share an SM and get ADJACENT stream-K
+                           // ranges, so their tile boundaries (epilogues) fall at different times
 };
 
 // ------------------------------------------------------------------------------------------
@@ -141,6 +154,18 @@ __device__ __forceinline__ void setmaxnreg_inc() {
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// named barrier over the consumer warps only (barrier 0 is __syncthreads)
+__device__ __forceinline__ void consumer_bar_sync(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
   double2 v;
@@ -218,6 +243,59 @@ __device__ __forceinline__ void tma_fill_operand(uint32_t dst, const CUtensorMap
 }
 
 // ------------------------------------------------------------------------------------------
+// Work schedule, shared by the producer and the consumers of a CTA
+// ------------------------------------------------------------------------------------------
+// A "segment" is a run of k-iterations [kb0, kb1) of one output tile.  CTA c of G first walks
+// its share of the stream-K region -- the contiguous run [S*c/G, S*(c+1)/G) of the region's
+// S = sk_tiles*kblocks iterations, which cuts into at most: the tail of one tile, some whole
+// tiles, the head of one tile -- and then whole tiles sk_tiles + c, sk_tiles + c + G, ...
+// With sk_tiles == 0 this is the plain persistent data-parallel schedule.
+struct Segment {
+  int64_t tile;
+  int kb0, kb1;
+};
+struct Schedule {
+  int64_t sk_it, sk_end;   // position / end inside the stream-K iteration space
+  int64_t dp_tile;         // next data-parallel tile
+  int64_t total_tiles;
+  int kblocks;
+  // Stream-K rank of this CTA.  The hardware places CTA b and b + #SMs on the same SM; giving
+  // them consecutive ranks staggers their phases inside a tile by one CTA share.
+  static __device__ __forceinline__ unsigned sk_rank(const GemmParams &p) {
+    const unsigned per_sm = gridDim.x / p.sk_sms;
+    if (per_sm * p.sk_sms != gridDim.x) return blockIdx.x;   // grid not a multiple of the SM count
+    return (blockIdx.x % p.sk_sms) * per_sm + blockIdx.x / p.sk_sms;
+  }
+  __device__ __forceinline__ Schedule(const GemmParams &p, int kblocks_) {
+    kblocks = kblocks_;
+    total_tiles = p.total_tiles;
+    const int64_t S = p.sk_tiles * kblocks;
+    const unsigned rank = sk_rank(p);
+    sk_it = S * rank / gridDim.x;
+    sk_end = S * (rank + 1) / gridDim.x;
+    dp_tile = p.sk_tiles + blockIdx.x;
+  }
+  __device__ __forceinline__ bool next(Segment &sg) {
+    if (sk_it < sk_end) {
+      sg.tile = sk_it / kblocks;
+      sg.kb0 = (int)(sk_it - sg.tile * kblocks);
+      const int64_t left = sk_end - sk_it;
+      sg.kb1 = (int)(left < (int64_t)(kblocks - sg.kb0) ? sg.kb0 + left : kblocks);
+      sk_it += sg.kb1 - sg.kb0;
+      return true;
+    }
+    if (dp_tile < total_tiles) {
+      sg.tile = dp_tile;
+      sg.kb0 = 0;
+      sg.kb1 = kblocks;
+      dp_tile += gridDim.x;
+      return true;
+    }
+    return false;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
 // The hot kernel
 // ------------------------------------------------------------------------------------------
 template <class Cfg, bool A_KMAJOR, bool B_KMAJOR>
@@ -226,6 +304,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
                           const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
   constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS, STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled TMA destinations need 1024-byte alignment.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -256,17 +335,19 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
 
   if (warp >= CONSUMER_WARPS) {
     // ===================== TMA producer (one elected lane) =====================
-    setmaxnreg_dec<Cfg::PRODUCER_REGS>();
+    if (Cfg::REGSPLIT) setmaxnreg_dec<Cfg::PRODUCER_REGS>();
     if (warp == CONSUMER_WARPS && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int b = (int)(tile / tiles_per_problem);
-        const int r = (int)(tile - (int64_t)b * tiles_per_problem);
+      Schedule sched(p, kblocks);
+      Segment sg;
+      while (sched.next(sg)) {
+        const int b = (int)(sg.tile / tiles_per_problem);
+        const int r = (int)(sg.tile - (int64_t)b * tiles_per_problem);
         const int m0 = (r % p.tiles_m) * BM;
         const int n0 = (r / p.tiles_m) * BN;
         const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           const uint32_t sA = smem_base + stage * STAGE_BYTES;
@@ -284,7 +365,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
   }
 
   // ===================== DMMA consumers =====================
-  setmaxnreg_inc<Cfg::CONSUMER_REGS>();
+  if (Cfg::REGSPLIT) setmaxnreg_inc<Cfg::CONSUMER_REGS>();
   const int g = lane >> 2, c = lane & 3;
   const int wm0 = (warp % Cfg::WARPS_M) * WM;  // warp's row offset inside the CTA tile
   const int wn0 = (warp / Cfg::WARPS_M) * WN;  // warp's column offset
@@ -293,20 +374,30 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
 
   int stage = 0;
   uint32_t phase = 0;
-  for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    const int b = (int)(tile / tiles_per_problem);
-    const int r = (int)(tile - (int64_t)b * tiles_per_problem);
-    const int m0 = (r % p.tiles_m) * BM;
-    const int n0 = (r / p.tiles_m) * BN;
-
+  uint32_t pending_bar = 0;  // empty barrier of the slot consumed last, not yet released
+  Schedule sched(p, kblocks);
+  Segment sg;
+  while (sched.next(sg)) {
     double acc[MB][NB][2];
 #pragma unroll
     for (int i = 0; i < MB; ++i)
 #pragma unroll
       for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int kb = 0; kb < kblocks; ++kb) {
+    for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
       mbar_wait(full_bar(stage), phase);
+      // Deferred slot release: the slot of the PREVIOUS k-iteration is handed back only now.
+      // An arrive issued right behind the loads of its own stage carries no scoreboard wait,
+      // and loads can sit in the memory pipeline for a long time behind another resident CTA's
+      // epilogue stores -- long enough for the producer to see the slot free and for the refill
+      // to land underneath them (observed on B200 as rare corrupted 16-row fragments whenever
+      // more than one CTA shared an SM).  At this point every DMMA of the previous iteration has
+      // been issued (in-order issue), so every LDS feeding them has returned its data.  Costs one
+      // slot of ring depth, no instructions.
+      if (pending_bar != 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pending_bar);
+      }
       const uint32_t sA = smem_base + stage * STAGE_BYTES;
       const uint32_t sB = sA + Cfg::A_BYTES;
 #pragma unroll
@@ -323,31 +414,125 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
 #pragma unroll
           for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], ao[i], bo[j]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar(stage));
+      pending_bar = empty_bar(stage);
       if (++stage == STAGES) {
         stage = 0;
         phase ^= 1u;
       }
     }
 
-    // ---- epilogue: registers -> global, C = alpha*acc + beta*C, bounds-predicated ----
+    // ---- stream-K fix-up -------------------------------------------------------------------
+    // A segment that does not start the tile publishes its partial sums (it is always the first
+    // thing this CTA computes).  The segment that starts a tile but does not finish it (always
+    // the last thing this CTA computes in the region) owns the tile: it adds, in CTA order, the
+    // partials of the CTAs that follow it -- published long before -- and writes C.
+    if (sg.kb0 != 0) {
+      const unsigned rank = Schedule::sk_rank(p);
+      double *ws = p.sk_workspace + (size_t)rank * (BM * BN) + threadIdx.x;
+#pragma unroll
+      for (int i = 0; i < MB; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) __stcg(ws + ((i * NB + j) * 2 + e) * CONSUMER_THREADS, acc[i][j][e]);
+      __threadfence();
+      consumer_bar_sync(CONSUMER_THREADS);
+      if (threadIdx.x == 0) st_release_gpu(p.sk_flags + rank, p.sk_epoch);
+      continue;
+    }
+    if (sg.kb1 != kblocks) {
+      const int64_t S = p.sk_tiles * kblocks;
+      const int64_t tile_end = (sg.tile + 1) * (int64_t)kblocks;
+      int covered = sg.kb1;
+      for (unsigned d = Schedule::sk_rank(p) + 1; covered < kblocks; ++d) {
+        const int64_t d0 = S * d / gridDim.x, d1 = S * (d + 1) / gridDim.x;
+        if (d1 == d0) continue;  // CTA d has no stream-K work (S < gridDim.x): nothing to wait for
+        if (threadIdx.x == 0) {
+          while (ld_acquire_gpu(p.sk_flags + d) != p.sk_epoch) {
+          }
+        }
+        consumer_bar_sync(CONSUMER_THREADS);
+        const double *ws = p.sk_workspace + (size_t)d * (BM * BN) + threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) acc[i][j][e] += __ldcg(ws + ((i * NB + j) * 2 + e) * CONSUMER_THREADS);
+        covered += (int)((d1 < tile_end ? d1 : tile_end) - d0);
+      }
+    }
+
+    // ---- epilogue: registers -> global, C = alpha*acc + beta*C ----
+    const int b = (int)(sg.tile / tiles_per_problem);
+    const int r = (int)(sg.tile - (int64_t)b * tiles_per_problem);
+    const int m0 = (r % p.tiles_m) * BM;
+    const int n0 = (r / p.tiles_m) * BN;
     double *Cb = p.C + (int64_t)b * p.stride_c;
     const bool use_beta = (p.beta != 0.0);
+    if (m0 + BM <= p.M && n0 + BN <= p.N) {
+      // Interior tile (CTA-uniform branch): no predicates, one base pointer per fragment column,
+      // rows at compile-time offsets.  With an MN-major A the row blocks 2jb / 2jb+1 hold
+      // adjacent rows 2g / 2g+1, so each pair goes out as one 16-byte store.
+      double *base = Cb + (int64_t)(n0 + wn0) * p.ldc + (m0 + wm0);
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
+      for (int j = 0; j < NB; ++j) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int64_t col = n0 + wn0 + frag_mn<B_KMAJOR>(j, 2 * c + e);
-        if (col < p.N) {
-          double *Ccol = Cb + col * p.ldc;
+        for (int e = 0; e < 2; ++e) {
+          double *pc = base + (int64_t)frag_mn<B_KMAJOR>(j, 2 * c + e) * p.ldc;
+          if (A_KMAJOR) {
+            pc += (g >> 1) + 4 * (g & 1);
 #pragma unroll
-          for (int i = 0; i < MB; ++i) {
-            const int64_t row = m0 + wm0 + frag_mn<A_KMAJOR>(i, g);
-            if (row < p.M) {
+            for (int i = 0; i < MB; ++i) {
               double v = p.alpha * acc[i][j][e];
-              if (use_beta) v += p.beta * Ccol[row];
-              Ccol[row] = v;
+              if (use_beta) v += p.beta * pc[8 * i];
+              pc[8 * i] = v;
+            }
+          } else {
+            pc += 2 * g;
+#pragma unroll
+            for (int ib = 0; ib < MB / 2; ++ib) {
+              double2 v;
+              v.x = p.alpha * acc[2 * ib][j][e];
+              v.y = p.alpha * acc[2 * ib + 1][j][e];
+              double2 *dst = reinterpret_cast<double2 *>(pc + 16 * ib);
+              if (use_beta) {
+                if (p.c_vec2) {
+                  const double2 o = *dst;
+                  v.x += p.beta * o.x;
+                  v.y += p.beta * o.y;
+                } else {
+                  v.x += p.beta * pc[16 * ib];
+                  v.y += p.beta * pc[16 * ib + 1];
+                }
+              }
+              if (p.c_vec2) {
+                *dst = v;
+              } else {
+                pc[16 * ib] = v.x;
+                pc[16 * ib + 1] = v.y;
+              }
+            }
+          }
+        }
+      }
+    } else {
+      // Edge tile: bounds-predicated element stores.
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int64_t col = n0 + wn0 + frag_mn<B_KMAJOR>(j, 2 * c + e);
+          if (col < p.N) {
+            double *Ccol = Cb + col * p.ldc;
+#pragma unroll
+            for (int i = 0; i < MB; ++i) {
+              const int64_t row = m0 + wm0 + frag_mn<A_KMAJOR>(i, g);
+              if (row < p.M) {
+                double v = p.alpha * acc[i][j][e];
+                if (use_beta) v += p.beta * Ccol[row];
+                Ccol[row] = v;
+              }
             }
           }
         }

@@ -216,6 +216,11 @@ struct ec_pipeline {
   StagingRing staging;
   StreamEngine *engine = nullptr;
   int cfg_chunk = 0, cfg_ring = 0, cfg_threads = 0;
+  // stream-K fix-up workspace (partial accumulator tiles + flags), allocated on first use
+  double *sk_workspace = nullptr;
+  unsigned *sk_flags = nullptr;
+  unsigned sk_epoch = 0;
+  int stream_k = 1;   // 0 disables the stream-K schedule (EC_STREAM_K=0)
 };
 
 struct ec_matrix {
@@ -295,19 +300,78 @@ int make_tensor_map(CUtensorMap *tm, const Operand &o, int64_t batch, int tile_e
   return EC_OK;
 }
 
+constexpr size_t SK_WORKSPACE_BYTES = (size_t)640 * 128 * 128 * 8 / 4;  // >= grid * BM*BN*8 for every config
+constexpr int SK_MAX_GRID = 1024;
+
+int ensure_sk_workspace(ec_pipeline *p) {
+  if (p->sk_workspace) return EC_OK;
+  EC_CUDA(cudaMalloc((void **)&p->sk_workspace, SK_WORKSPACE_BYTES));
+  EC_CUDA(cudaMalloc((void **)&p->sk_flags, SK_MAX_GRID * sizeof(unsigned)));
+  EC_CUDA(cudaMemsetAsync(p->sk_flags, 0, SK_MAX_GRID * sizeof(unsigned), p->stream));
+  return EC_OK;
+}
+
+// Resident CTAs per SM of one kernel instantiation on one device (cached).
+template <class Cfg, bool AK, bool BK_>
+int ctas_per_sm(ec_pipeline *p, int *out) {
+  auto kern = ec::dgemm_tma_dmma_kernel<Cfg, AK, BK_>;
+  static std::atomic<int> cached[64];
+  int v = cached[p->device & 63].load();
+  if (v == 0) {
+    EC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int occ = 0;
+    EC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM_BYTES));
+    if (occ < 1) return fail(EC_ERR_CUDA, "kernel does not fit on an SM (occupancy 0)");
+    v = std::min(occ, Cfg::MIN_CTAS);
+    cached[p->device & 63].store(v);
+  }
+  *out = v;
+  return EC_OK;
+}
+
 template <class Cfg, bool AK, bool BK_>
 int launch_tma_dmma(ec_pipeline *p, const CUtensorMap &tmA, const CUtensorMap &tmB,
-                    const ec::GemmParams &gp) {
+                    ec::GemmParams &gp, bool want_sk) {
   auto kern = ec::dgemm_tma_dmma_kernel<Cfg, AK, BK_>;
-  static std::atomic<uint64_t> configured{0};  // per instantiation, one bit per device
-  const uint64_t bit = 1ull << (p->device & 63);
-  if (!(configured.load() & bit)) {
-    EC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::SMEM_BYTES));
-    configured.fetch_or(bit);
+  int ctas = 1;
+  int rc = ctas_per_sm<Cfg, AK, BK_>(p, &ctas);
+  if (rc) return rc;
+  const int64_t slots = (int64_t)p->sm_count * ctas;
+  const int64_t kblocks = (gp.K + ec::BK - 1) / ec::BK;
+  int grid = (int)std::min<int64_t>(gp.total_tiles, slots);
+  gp.sk_tiles = 0;
+  gp.sk_sms = p->sm_count;
+  gp.sk_workspace = nullptr;
+  gp.sk_flags = nullptr;
+  gp.sk_epoch = 0;
+  // Stream-K region: the tiles of the last, partial wave plus (when there is one) one full wave,
+  // so that every CTA gets between one and two tiles' worth of k-iterations in the region.
+  const int64_t rem = gp.total_tiles % slots;
+  if (want_sk && p->stream_k && (rem != 0 || getenv("EC_SK_ALL")) && slots <= SK_MAX_GRID &&
+      slots * (int64_t)(Cfg::BM * Cfg::BN * 8) <= (int64_t)SK_WORKSPACE_BYTES) {
+    int64_t sk_tiles = rem + (gp.total_tiles > slots ? slots : 0);
+    if (const char *e = getenv("EC_SK_ALL")) {   // experiment: stream-K over every tile
+      if (atoi(e)) sk_tiles = gp.total_tiles;
+    }
+    if (sk_tiles * kblocks >= 4 * slots) {   // at least 4 k-iterations per CTA in the region
+      rc = ensure_sk_workspace(p);
+      if (rc) return rc;
+      gp.sk_tiles = sk_tiles;
+      gp.sk_workspace = p->sk_workspace;
+      gp.sk_flags = p->sk_flags;
+      gp.sk_epoch = ++p->sk_epoch;
+      if (gp.sk_epoch == 0) gp.sk_epoch = ++p->sk_epoch;   // 0 is the cleared state
+      grid = (int)slots;
+    }
   }
-  const int grid = (int)std::min<int64_t>(gp.total_tiles, (int64_t)p->sm_count * Cfg::MIN_CTAS);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, p->stream>>>(tmA, tmB, gp);
+  if (gp.sk_tiles > 0) {
+    // CTAs wait on one another's partials: a cooperative launch guarantees co-residency.
+    void *args[3] = {(void *)&tmA, (void *)&tmB, (void *)&gp};
+    EC_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(Cfg::THREADS), args,
+                                        (size_t)Cfg::SMEM_BYTES, p->stream));
+  } else {
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, p->stream>>>(tmA, tmB, gp);
+  }
   EC_CUDA(cudaGetLastError());
   p->launches++;
   return EC_OK;
@@ -316,7 +380,8 @@ int launch_tma_dmma(ec_pipeline *p, const CUtensorMap &tmA, const CUtensorMap &t
 template <class Cfg>
 int run_tma_dmma(ec_pipeline *p, const Operand &oa, const Operand &ob, int64_t m, int64_t n,
                  int64_t k, double alpha, double beta, double *C, int64_t ldc, int64_t stride_c,
-                 int64_t stride_a, int64_t stride_b, int64_t batch, const char *const names[4]) {
+                 int64_t stride_a, int64_t stride_b, int64_t batch, bool want_sk,
+                 const char *const names[8]) {
   CUtensorMap tmA, tmB;
   int rc = make_tensor_map(&tmA, oa, batch, Cfg::BM);
   if (rc) return rc;
@@ -331,43 +396,59 @@ int run_tma_dmma(ec_pipeline *p, const Operand &oa, const Operand &ob, int64_t m
   gp.total_tiles = (int64_t)gp.tiles_m * gp.tiles_n * batch;
   gp.a_batched = (batch > 1 && stride_a != 0);
   gp.b_batched = (batch > 1 && stride_b != 0);
-  if (oa.kmajor && ob.kmajor) { p->last_kernel = names[0]; return launch_tma_dmma<Cfg, true, true>(p, tmA, tmB, gp); }
-  if (oa.kmajor && !ob.kmajor) { p->last_kernel = names[1]; return launch_tma_dmma<Cfg, true, false>(p, tmA, tmB, gp); }
-  if (!oa.kmajor && ob.kmajor) { p->last_kernel = names[2]; return launch_tma_dmma<Cfg, false, true>(p, tmA, tmB, gp); }
-  p->last_kernel = names[3];
-  return launch_tma_dmma<Cfg, false, false>(p, tmA, tmB, gp);
+  gp.c_vec2 = (((uintptr_t)C & 15u) == 0 && (ldc & 1) == 0 && (batch <= 1 || (stride_c & 1) == 0)) ? 1 : 0;
+  int idx;
+  if (oa.kmajor && ob.kmajor) { idx = 0; rc = launch_tma_dmma<Cfg, true, true>(p, tmA, tmB, gp, want_sk); }
+  else if (oa.kmajor && !ob.kmajor) { idx = 1; rc = launch_tma_dmma<Cfg, true, false>(p, tmA, tmB, gp, want_sk); }
+  else if (!oa.kmajor && ob.kmajor) { idx = 2; rc = launch_tma_dmma<Cfg, false, true>(p, tmA, tmB, gp, want_sk); }
+  else { idx = 3; rc = launch_tma_dmma<Cfg, false, false>(p, tmA, tmB, gp, want_sk); }
+  p->last_kernel = names[idx + (gp.sk_tiles > 0 ? 4 : 0)];
+  return rc;
 }
 
-// Tile choice.  All configurations run the DMMA pipe at the same rate once it is fed; what
-// differs is (a) load balance -- the per-SM pipe time is ceil(tiles / SMs) tiles' worth, so
-// finer tiles waste less on the last wave -- and (b) per-tile overhead (prologue/epilogue), which
-// configurations with >= 2 CTAs per SM hide behind the other CTA's main loop.  Cost model in SM
-// clocks; the constants come from the tile sweep in profiles/ (tools/tile_sweep.py).
-enum { TILE_AUTO = 0, TILE_L = 1, TILE_M = 2, TILE_S = 3, TILE_XS = 4 };
+// Tile and schedule choice.  All configurations run the DMMA pipe at nearly the same rate once
+// it is fed; what differs is (a) load balance -- under the data-parallel schedule the busiest SM
+// does ceil(tiles / SMs) tiles, under stream-K every SM does tiles / SMs of them plus one
+// workspace round trip -- and (b) per-tile overhead and main-loop efficiency, which get worse
+// as tiles shrink.  Cost model in SM clocks, fitted to profiles/r01_tile_sweep*.json.
+enum { TILE_AUTO = 0, TILE_L = 1, TILE_S = 2, TILE_XS = 3 };
 
-int choose_tile(const ec_pipeline *p, int64_t m, int64_t n, int64_t k, int64_t batch) {
-  // EC_FORCE_TILE=1..4 overrides the choice (tools/tile_sweep.py); read per call, it is cheap
-  if (const char *e = getenv("EC_FORCE_TILE")) {
-    const int f = atoi(e);
-    if (f >= TILE_L && f <= TILE_XS) return f;
+struct TileChoice { int tile; bool sk; };
+
+TileChoice choose_tile(const ec_pipeline *p, int64_t m, int64_t n, int64_t k, int64_t batch) {
+  int force = 0;
+  bool allow_sk = p->stream_k != 0, force_sk = false;
+  // EC_FORCE_TILE=1..4 and EC_STREAM_K=0 (never) | 1 (cost model) | 2 (whenever feasible) override
+  // the choice for tools/tile_sweep.py and the tests; read per call
+  if (const char *e = getenv("EC_FORCE_TILE")) force = atoi(e);
+  if (const char *e = getenv("EC_STREAM_K")) {
+    allow_sk = atoi(e) != 0;
+    force_sk = atoi(e) == 2;
   }
-  struct Cand { int id, bm, bn, ctas; double eff, overhead; };
-  // eff: fraction of the DMMA issue rate the main loop sustains; overhead: exposed clocks per tile
-  // fitted to profiles/r01_tile_sweep.json (B200): L sustains 98.7 % of the issue rate in the
-  // main loop with ~3.3k exposed clocks per tile; the finer tiles trade main-loop efficiency
-  // (more LDS per DMMA) for balance; two CTAs per SM run in lockstep and hide less than hoped
-  const Cand cands[4] = {{TILE_L, 128, 128, 1, 0.987, 3300.0},
-                         {TILE_M, 128, 64, 2, 0.985, 2600.0},
-                         {TILE_S, 64, 64, 3, 0.955, 1500.0},
-                         {TILE_XS, 64, 32, 4, 0.93, 1000.0}};
+  // eff: fraction of the DMMA issue rate the main loop sustains; overhead: exposed clocks per
+  // tile; fixup: exposed clocks of one stream-K tail (publish partial, wait, read, epilogue)
+  struct Cand { int id, bm, bn, ctas; double eff, overhead, fixup; };
+  const Cand cands[3] = {{TILE_L, 128, 128, 1, 0.987, 2300.0, 30000.0},
+                         {TILE_S, 64, 64, 2, 0.955, 1200.0, 12000.0},
+                         {TILE_XS, 64, 32, 3, 0.90, 800.0, 8000.0}};
+  const double kpad = (double)((k + 15) / 16 * 16);
+  const int64_t kblocks = (k + 15) / 16;
   double best = 1e300;
-  int pick = TILE_M;
+  TileChoice pick{TILE_L, false};
   for (const Cand &c : cands) {
+    if (force >= TILE_L && force <= TILE_XS && c.id != force) continue;
     const int64_t tiles = ((m + c.bm - 1) / c.bm) * ((n + c.bn - 1) / c.bn) * batch;
-    const int64_t per_sm = (tiles + p->sm_count - 1) / p->sm_count;   // tiles on the busiest SM
-    const double tile_clk = (double)c.bm * c.bn * (double)((k + 15) / 16 * 16) / 64.0 / c.eff + c.overhead;
-    const double cost = per_sm * tile_clk;
-    if (cost < best) { best = cost; pick = c.id; }
+    const int64_t slots = (int64_t)p->sm_count * c.ctas;
+    const double tile_clk = (double)c.bm * c.bn * kpad / 64.0 / c.eff + c.overhead;
+    const double dp = (double)((tiles + p->sm_count - 1) / p->sm_count) * tile_clk;
+    if (dp < best) { best = dp; pick = {c.id, false}; }
+    const int64_t rem = tiles % slots;
+    const int64_t sk_tiles = rem + (tiles > slots ? slots : 0);
+    if (allow_sk && rem != 0 && sk_tiles * kblocks >= 4 * slots) {
+      // every SM does its exact share; one partial tile written and one read per CTA
+      const double sk = force_sk ? dp * 1e-3 : (double)tiles / p->sm_count * tile_clk + c.fixup;
+      if (sk < best) { best = sk; pick = {c.id, true}; }
+    }
   }
   return pick;
 }
@@ -407,15 +488,17 @@ int dgemm_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
   const bool big_enough = (m >= 32 && n >= 32 && k >= 16) && (m * n * k >= (int64_t)64 * 64 * 64);
   const bool c_ok = m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31);
   if (big_enough && c_ok && tma_ok(oa, batch) && tma_ok(ob, batch)) {
-    static const char *const nL[4] = {"tma_dmma_TN", "tma_dmma_TT", "tma_dmma_NN", "tma_dmma_NT"};
-    static const char *const nM[4] = {"tma_dmma_TN_m", "tma_dmma_TT_m", "tma_dmma_NN_m", "tma_dmma_NT_m"};
-    static const char *const nS[4] = {"tma_dmma_TN_s", "tma_dmma_TT_s", "tma_dmma_NN_s", "tma_dmma_NT_s"};
-    static const char *const nX[4] = {"tma_dmma_TN_xs", "tma_dmma_TT_xs", "tma_dmma_NN_xs", "tma_dmma_NT_xs"};
-    switch (choose_tile(p, m, n, k, batch)) {
-      case TILE_L: return run_tma_dmma<ec::CfgL>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, nL);
-      case TILE_S: return run_tma_dmma<ec::CfgS>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, nS);
-      case TILE_XS: return run_tma_dmma<ec::CfgXS>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, nX);
-      default: return run_tma_dmma<ec::CfgM>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, nM);
+    static const char *const nL[8] = {"tma_dmma_TN", "tma_dmma_TT", "tma_dmma_NN", "tma_dmma_NT",
+                                      "tma_dmma_TN_sk", "tma_dmma_TT_sk", "tma_dmma_NN_sk", "tma_dmma_NT_sk"};
+    static const char *const nS[8] = {"tma_dmma_TN_s", "tma_dmma_TT_s", "tma_dmma_NN_s", "tma_dmma_NT_s",
+                                      "tma_dmma_TN_s_sk", "tma_dmma_TT_s_sk", "tma_dmma_NN_s_sk", "tma_dmma_NT_s_sk"};
+    static const char *const nX[8] = {"tma_dmma_TN_xs", "tma_dmma_TT_xs", "tma_dmma_NN_xs", "tma_dmma_NT_xs",
+                                      "tma_dmma_TN_xs_sk", "tma_dmma_TT_xs_sk", "tma_dmma_NN_xs_sk", "tma_dmma_NT_xs_sk"};
+    const TileChoice ch = choose_tile(p, m, n, k, batch);
+    switch (ch.tile) {
+      case TILE_S: return run_tma_dmma<ec::CfgS>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nS);
+      case TILE_XS: return run_tma_dmma<ec::CfgXS>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nX);
+      default: return run_tma_dmma<ec::CfgL>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nL);
     }
   }
 
@@ -718,6 +801,8 @@ int ec_pipeline_destroy(ec_pipeline *p) {
     delete p->engine;
   }
   p->staging.destroy();
+  if (p->sk_workspace) cudaFree(p->sk_workspace);
+  if (p->sk_flags) cudaFree(p->sk_flags);
   if (p->owns_stream) cudaStreamDestroy(p->stream);
   delete p;
   return EC_OK;

@@ -204,16 +204,81 @@ def test_dgemm_simt_kernel_odd_shapes(pipe, ta, tb, shape):
     assert orc.rel_frobenius(got, want) <= TOL
 
 
-@pytest.mark.parametrize("tile", [1, 2, 3, 4])
+@pytest.mark.parametrize("tile", [1, 2, 3])
 @pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
 def test_every_tile_configuration(pipe, tile, ta, tb, monkeypatch):
-    """The four CTA tile shapes (128x128, 128x64, 64x64, 64x32) compute the same product."""
+    """The three CTA tile shapes (128x128, 64x64, 64x32) compute the same product."""
     monkeypatch.setenv("EC_FORCE_TILE", str(tile))
     for (m, n, k) in [(256, 192, 144), (130, 70, 50), (520, 264, 1030)]:
         got, want = run_dgemm(pipe, ta, tb, m, n, k, 1.25, -0.5, seed=tile + m)
-        suffix = {1: "", 2: "_m", 3: "_s", 4: "_xs"}[tile]
-        assert pipe.last_kernel() == "tma_dmma_" + ("T" if ta else "N") + ("T" if tb else "N") + suffix
+        suffix = {1: "", 2: "_s", 3: "_xs"}[tile]
+        name = "tma_dmma_" + ("T" if ta else "N") + ("T" if tb else "N") + suffix
+        assert pipe.last_kernel() in (name, name + "_sk")
         assert orc.rel_frobenius(got, want) <= TOL
+
+
+@pytest.mark.parametrize("tile", [1, 2, 3])
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, True)])
+def test_stream_k_schedule(pipe, tile, ta, tb, monkeypatch):
+    """Shapes whose tile count does not fill the last wave take the stream-K schedule: partial
+    sums cross CTAs through the workspace, the owner adds them in CTA order.  Same bar, and the
+    result is bit-reproducible from run to run (the fix-up order is fixed)."""
+    monkeypatch.setenv("EC_FORCE_TILE", str(tile))
+    monkeypatch.setenv("EC_STREAM_K", "2")     # stream-K whenever feasible, not only when cheaper
+    for (m, n, k) in [(1280, 1280, 512), (900, 1100, 2000), (1536, 1024, 160)]:
+        got, want = run_dgemm(pipe, ta, tb, m, n, k, 1.0, 0.5, seed=tile)
+        assert pipe.last_kernel().endswith("_sk"), (pipe.last_kernel(), m, n, k)
+        assert orc.rel_frobenius(got, want) <= TOL
+        again, _ = run_dgemm(pipe, ta, tb, m, n, k, 1.0, 0.5, seed=tile)
+        assert np.array_equal(got, again)
+    monkeypatch.setenv("EC_STREAM_K", "0")
+    got0, want = run_dgemm(pipe, ta, tb, 1280, 1280, 512, 1.0, 0.5, seed=tile)
+    assert not pipe.last_kernel().endswith("_sk")
+    assert orc.rel_frobenius(got0, want) <= TOL
+
+
+def test_slot_release_race_regression(pipe, monkeypatch):
+    """Regression: with several CTAs per SM, a consumer's empty-barrier arrive used to be able
+    to overtake its own in-flight LDS (queued behind another CTA's epilogue stores), letting the
+    TMA refill land under the loads -- rare corrupted 16-row fragments.  Every tile configuration
+    must reproduce the 128x128 configuration's result BIT FOR BIT on a long batched run (the
+    per-element summation order does not depend on the tile shape)."""
+    n, batch = 512, 600
+    dT = ec.CudaMatrix(n, n * batch, pipe.get_stream())
+    dF = ec.CudaMatrix(n, n, pipe.get_stream())
+    pipe.fill_uniform(orc.SEED, 1, dT.data(), n * n, batch)
+    pipe.fill_uniform(orc.SEED, 0, dF.data(), n * n, 1)
+    monkeypatch.setenv("EC_STREAM_K", "0")
+
+    def run(tile):
+        monkeypatch.setenv("EC_FORCE_TILE", str(tile))
+        dR = ec.CudaMatrix(n, n * batch, pipe.get_stream())
+        pipe.dgemm_strided_batched(0, 0, n, n, n, 1.0, dT.data(), n, n * n, dF.data(), n, 0, 0.0, dR.data(), n, n * n, batch)
+        return dR.to_eigen()
+
+    want = run(1)
+    F = orc.fill_uniform(orc.SEED, 0, (n, n))
+    assert orc.rel_frobenius(want[:, :n], orc.cpu_product(orc.fill_uniform(orc.SEED, 1, (n, n)), F)) <= TOL
+    for tile in (2, 3):
+        for _ in range(4):
+            assert np.array_equal(run(tile), want), f"tile configuration {tile} diverged"
+
+
+def test_stream_k_batched(pipe, monkeypatch):
+    """The tensor-stream shape with a batch that leaves a partial last wave."""
+    monkeypatch.setenv("EC_STREAM_K", "2")
+    n, batch = 256, 41
+    dT = ec.CudaMatrix(n, n * batch, pipe.get_stream())
+    dF = ec.CudaMatrix(n, n, pipe.get_stream())
+    dR = ec.CudaMatrix(n, n * batch, pipe.get_stream())
+    pipe.fill_uniform(orc.SEED, 1, dT.data(), n * n, batch)
+    pipe.fill_uniform(orc.SEED, 0, dF.data(), n * n, 1)
+    pipe.dgemm_strided_batched(0, 0, n, n, n, 1.0, dT.data(), n, n * n, dF.data(), n, 0, 0.0, dR.data(), n, n * n, batch)
+    assert pipe.last_kernel().endswith("_sk"), pipe.last_kernel()
+    got = dR.to_eigen().reshape(n, n, batch, order="F")
+    F = orc.fill_uniform(orc.SEED, 0, (n, n))
+    for i in range(batch):
+        assert orc.rel_frobenius(got[:, :, i], orc.cpu_product(orc.fill_uniform(orc.SEED, i + 1, (n, n)), F)) <= TOL
 
 
 def test_beta_zero_ignores_nan_in_c(pipe):

@@ -14,7 +14,7 @@ import eigencuda_b200 as ec
 dev = torch.device("cuda", 0)
 stream = torch.cuda.current_stream()
 pipe = ec.CudaPipeline(0, stream=stream.cuda_stream)
-NAMES = {0: "auto", 1: "L128x128", 2: "M128x64", 3: "S64x64", 4: "XS64x32"}
+NAMES = {-1: "auto_nosk", 0: "auto", 1: "L128x128", 2: "S64x64", 3: "XS64x32"}
 
 
 def timed(fn, reps):
@@ -33,7 +33,7 @@ def timed(fn, reps):
 
 
 out = {"square": [], "batched": []}
-sizes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [256, 512, 1024, 2048, 4096, 8192]
+sizes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [256, 512, 768, 1024, 1536, 2048, 3072, 4096, 8192]
 for n in sizes:
     A = torch.empty(n * n, dtype=torch.float64, device=dev)
     B = torch.empty(n * n, dtype=torch.float64, device=dev)
@@ -47,12 +47,13 @@ for n in sizes:
         Am, Bm = A.view(n, n).T, B.view(n, n).T
         ref = (Am @ Bm)
     row = {"n": n}
-    for tile in (0, 1, 2, 3, 4):
-        if tile:
+    for tile in (-1, 0, 1, 2, 3):
+        os.environ["EC_STREAM_K"] = "0" if tile < 0 else "1"
+        if tile > 0:
             os.environ["EC_FORCE_TILE"] = str(tile)
         else:
             os.environ.pop("EC_FORCE_TILE", None)
-        if tile == 1 and n < 128 or tile == 4 and n > 4096:
+        if tile == 1 and n < 128 or tile == 3 and n > 4096:
             continue
         fn = lambda: pipe.dgemm(0, 0, n, n, n, 1.0, A.data_ptr(), n, B.data_ptr(), n, 0.0, Cm.data_ptr(), n)
         ms = timed(fn, 3 if n >= 8192 else 10)
@@ -70,8 +71,9 @@ for n, batch in [(512, 64), (512, 1024), (512, 4096), (1000, 256), (256, 4096), 
     pipe.fill_uniform(1, 1, A.data_ptr(), n * n, batch)
     pipe.fill_uniform(1, 0, B.data_ptr(), n * n, 1)
     row = {"n": n, "batch": batch}
-    for tile in (0, 1, 2, 3, 4):
-        if tile:
+    for tile in (-1, 0, 1, 2, 3):
+        os.environ["EC_STREAM_K"] = "0" if tile < 0 else "1"
+        if tile > 0:
             os.environ["EC_FORCE_TILE"] = str(tile)
         else:
             os.environ.pop("EC_FORCE_TILE", None)
@@ -83,4 +85,5 @@ for n, batch in [(512, 64), (512, 1024), (512, 4096), (1000, 256), (256, 4096), 
     out["batched"].append(row)
     del A, B, Cm
 os.environ.pop("EC_FORCE_TILE", None)
+os.environ.pop("EC_STREAM_K", None)
 print(json.dumps(out))
