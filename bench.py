@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--no-peaks", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-sample", type=int, default=512, help="matrices per step for --impl reference")
+    ap.add_argument("--no-extras", action="store_true", help="skip configs[3] (transposed / basis transform) and the pageable e2e")
     ap.add_argument("--chunk", type=int, default=0, help="tensor-stream engine: matrices per device chunk (0 = default)")
     ap.add_argument("--ring", type=int, default=0, help="tensor-stream engine: ring depth (0 = default)")
     return ap.parse_args()
@@ -286,6 +287,7 @@ def main():
     torch.cuda.synchronize()
     barrier()
     launches = pipe.launch_count() - l0
+    kernel_name = pipe.last_kernel()
     total_ms = evs[0].elapsed_time(evs[-1])
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     clocks = sampler.stop() if rank == 0 else None
@@ -367,14 +369,14 @@ def main():
         sweep = []
         del T, R
         torch.cuda.empty_cache()
-        for nn in (1024, 2048, 4096, 8192):
+        for nn in (512, 1024, 2048, 4096, 8192, 16384):
             A = torch.empty(nn * nn, dtype=torch.float64, device=dev)
             B = torch.empty(nn * nn, dtype=torch.float64, device=dev)
             Cm = torch.empty(nn * nn, dtype=torch.float64, device=dev)
             pipe.fill_uniform(SEED, 0, A.data_ptr(), nn * nn, 1)
             pipe.fill_uniform(SEED, 1, B.data_ptr(), nn * nn, 1)
-            reps = 3 if nn >= 8192 else 10
-            for _ in range(3):
+            reps = 2 if nn >= 16384 else 3 if nn >= 8192 else 10
+            for _ in range(1 if nn >= 16384 else 3):
                 pipe.dgemm(0, 0, nn, nn, nn, 1.0, A.data_ptr(), nn, B.data_ptr(), nn, 0.0, Cm.data_ptr(), nn)
             best = float("inf")
             for _ in range(reps):
@@ -385,8 +387,79 @@ def main():
                 b.synchronize()
                 best = min(best, a.elapsed_time(b))
             tf = 2.0 * nn ** 3 / (best * 1e-3) / 1e12
-            sweep.append({"n": nn, "ms": best, "tflops": tf, "frac_of_datasheet_fp64": tf / FP64_DATASHEET_TFLOPS})
+            sweep.append({"n": nn, "ms": best, "tflops": tf, "frac_of_datasheet_fp64": tf / FP64_DATASHEET_TFLOPS,
+                          "kernel": pipe.last_kernel()})
             del A, B, Cm
+
+    # ---- extras (rank 0, N=1): configs[3] and the pageable-host variant of the e2e leg ----
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = {}
+        torch.cuda.empty_cache()
+        # configs[3]: 2000 x (1000x1000): A^T * B_i and A^T * M_i * A, resident in HBM
+        n4, c4 = 1000, 2000
+        F4 = torch.empty(n4 * n4, dtype=torch.float64, device=dev)
+        T4 = torch.empty(c4 * n4 * n4, dtype=torch.float64, device=dev)
+        R4 = torch.empty(c4 * n4 * n4, dtype=torch.float64, device=dev)
+        pipe.fill_uniform(SEED, 0, F4.data_ptr(), n4 * n4, 1)
+        pipe.fill_uniform(SEED, 1, T4.data_ptr(), n4 * n4, c4)
+        for name, kind, gemms in (("left_t (A^T * B_i)", ec.EC_STREAM_LEFT_T, 1), ("basis (A^T * M_i * A)", ec.EC_STREAM_BASIS, 2)):
+            run = lambda: pipe.tensor_stream_device(kind, F4.data_ptr(), n4, n4, T4.data_ptr(), R4.data_ptr(), c4, n4, n4)
+            for _ in range(2):
+                run()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            a.record(stream)
+            for _ in range(reps):
+                run()
+            b.record(stream)
+            b.synchronize()
+            ms = a.elapsed_time(b) / reps
+            tf = c4 * gemms * 2.0 * n4 ** 3 / (ms * 1e-3) / 1e12
+            extras[name] = {"matrices": c4, "n": n4, "ms_per_step": ms, "matrices_per_s": c4 / (ms * 1e-3),
+                            "tflops": tf, "frac_of_fp64_peak": tf / FP64_DATASHEET_TFLOPS, "resident": True}
+        # e2e for the basis transform through the C ABI, pinned host memory (512 matrices)
+        ce = 512
+        pin_in4, pin_out4 = ec.PinnedBuffer((n4 * n4, ce)), ec.PinnedBuffer((n4 * n4, ce))
+        torch.from_numpy(pin_in4.array.reshape(-1, order="F")).copy_(T4[: ce * n4 * n4])
+        torch.cuda.synchronize()
+        ip = (C.c_void_p * ce)(*[pin_in4.ptr + 8 * n4 * n4 * i for i in range(ce)])
+        op = (C.c_void_p * ce)(*[pin_out4.ptr + 8 * n4 * n4 * i for i in range(ce)])
+        pipe.set_stream_config(0, 0, 0)
+        for name, kind, gemms in (("left_t_e2e", ec.EC_STREAM_LEFT_T, 1), ("basis_e2e", ec.EC_STREAM_BASIS, 2)):
+            pipe.tensor_stream_raw(kind, F4.data_ptr(), n4, n4, ip, op, ce, n4, n4)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                pipe.tensor_stream_raw(kind, F4.data_ptr(), n4, n4, ip, op, ce, n4, n4)
+            dt = (time.perf_counter() - t0) / 2
+            extras[name] = {"matrices": ce, "n": n4, "ms_per_step": 1e3 * dt, "matrices_per_s": ce / dt,
+                            "tflops": ce * gemms * 2.0 * n4 ** 3 / dt / 1e12,
+                            "link_gbs_each_way": ce * n4 * n4 * 8 / dt / 1e9, "host_memory": "pinned"}
+        pin_in4.close()
+        pin_out4.close()
+        del F4, T4, R4
+        torch.cuda.empty_cache()
+        # the main workload from PAGEABLE host memory (what a std::vector<Eigen::MatrixXd> is):
+        # staged through the engine's pinned ring by worker threads
+        cp_ = 1024
+        Fh = np.asfortranarray(F.cpu().numpy().reshape(n, n, order="F"))
+        base = np.empty((elems, cp_), dtype=np.float64, order="F")
+        Tsrc = torch.empty(cp_ * elems, dtype=torch.float64, device=dev)
+        pipe.fill_uniform(SEED, 1, Tsrc.data_ptr(), elems, cp_)
+        torch.from_numpy(base.reshape(-1, order="F")).copy_(Tsrc)
+        outs = np.empty((elems, cp_), dtype=np.float64, order="F")
+        ipp = (C.c_void_p * cp_)(*[base.ctypes.data + 8 * elems * i for i in range(cp_)])
+        opp = (C.c_void_p * cp_)(*[outs.ctypes.data + 8 * elems * i for i in range(cp_)])
+        pipe.tensor_stream_raw(ec.EC_STREAM_RIGHT, Fh.ctypes.data, n, n, ipp, opp, cp_, n, n)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            pipe.tensor_stream_raw(ec.EC_STREAM_RIGHT, Fh.ctypes.data, n, n, ipp, opp, cp_, n, n)
+        dt = (time.perf_counter() - t0) / 2
+        extras["e2e_pageable"] = {"matrices": cp_, "n": n, "ms_per_step": 1e3 * dt, "matrices_per_s": cp_ / dt,
+                                  "host_gbs_each_way": cp_ * elems * 8 / dt / 1e9,
+                                  "host_memory": "pageable, staged through pinned ring by worker threads"}
+        del Tsrc, base, outs
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -404,7 +477,7 @@ def main():
                 traffic = None
         roofline = {"bound": "tensor", "achieved": achieved_tflops, "peak": FP64_DATASHEET_TFLOPS,
                     "unit": "TFLOP/s", "frac": achieved_tflops / FP64_DATASHEET_TFLOPS, "traffic": traffic,
-                    "kernel": "dgemm_tma_dmma_kernel<NN> (FP64 DMMA, mma.sync.m8n8k4)",
+                    "kernel": "dgemm_tma_dmma_kernel<CfgL,NN> (FP64 DMMA, mma.sync.m8n8k4), variant " + kernel_name,
                     "kernel_ms": kernel_ms, "launches_per_step": launches / args.steps,
                     "algorithmic_flops_per_launch": count * flops_per_matrix,
                     "algorithmic_hbm_bytes_per_launch": count * 2 * elems * 8 + elems * 8,
@@ -428,7 +501,7 @@ def main():
                            "generator": "splitmix64 counter-based, seed 20200210"},
                 "tflops": value * flops_per_matrix / 1e12,
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu, "dgemm": sweep, "peaks": peaks,
+                "cpu_baseline": cpu, "dgemm": sweep, "extras": extras, "peaks": peaks,
                 "parity_rel_frobenius": err}
         print(json.dumps(line), flush=True)
     pipe.close()

@@ -54,6 +54,7 @@ SIGNATURES = {
     "ec_host_free": (_int, [_vp]),
     "ec_fill_uniform": (_int, [_vp, _u64, _u64, _dp, _i64]),
     "ec_fill_uniform_batched": (_int, [_vp, _u64, _u64, _dp, _i64, _i64]),
+    "ec_fill_uniform_block": (_int, [_vp, _u64, _u64, _dp, _i64, _i64, _i64, _i64, _i64, _i64]),
     "ec_pipeline_launch_count": (_i64, [_vp]),
     "ec_pipeline_last_kernel": (C.c_char_p, [_vp]),
 }

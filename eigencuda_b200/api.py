@@ -195,6 +195,10 @@ class CudaPipeline:
     def fill_uniform(self, seed, first_id, dst, count, batch=1):
         check(lib.ec_fill_uniform_batched(self._h, seed, first_id, int(dst), count, batch))
 
+    def fill_uniform_block(self, seed, matrix_id, dst, rows, cols, ld_dst, row0, col0, global_ld):
+        check(lib.ec_fill_uniform_block(self._h, seed, matrix_id, int(dst), rows, cols, ld_dst, row0,
+                                        col0, global_ld))
+
     def launch_count(self):
         return int(lib.ec_pipeline_launch_count(self._h))
 

@@ -659,4 +659,19 @@ __global__ void fill_uniform_kernel(uint64_t seed, uint64_t first_id, double *ds
   }
 }
 
+__global__ void fill_uniform_block_kernel(uint64_t seed, uint64_t matrix_id, double *dst, int64_t rows,
+                                          int64_t cols, int64_t ld_dst, int64_t row0, int64_t col0,
+                                          int64_t global_ld) {
+  const int64_t total = rows * cols;
+  const uint64_t key = splitmix64(seed ^ splitmix64(matrix_id + 0x632BE59BD9B4E019ULL));
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = idx / rows, i = idx - j * rows;
+    const uint64_t gi = (uint64_t)((col0 + j) * global_ld + (row0 + i));
+    const uint64_t rnd = splitmix64(key + gi * 0xD1342543DE82EF95ULL);
+    const double u = (double)(rnd >> 11) * (1.0 / 9007199254740992.0);
+    dst[j * ld_dst + i] = 2.0 * u - 1.0;
+  }
+}
+
 }  // namespace ec

@@ -1286,6 +1286,23 @@ int ec_fill_uniform_batched(ec_pipeline *p, uint64_t seed, uint64_t first_id, do
   p->launches++;
   return EC_OK;
 }
+int ec_fill_uniform_block(ec_pipeline *p, uint64_t seed, uint64_t matrix_id, double *dst,
+                          int64_t rows, int64_t cols, int64_t ld_dst, int64_t row0, int64_t col0,
+                          int64_t global_ld) {
+  if (!p) return fail(EC_ERR_ARG, "null pipeline");
+  if (rows < 0 || cols < 0 || row0 < 0 || col0 < 0 || ld_dst < rows || global_ld < row0 + rows)
+    return fail(EC_ERR_ARG, "bad block geometry");
+  if (rows == 0 || cols == 0) return EC_OK;
+  if (!dst) return fail(EC_ERR_ARG, "null destination");
+  DeviceGuard guard(p->device);
+  const int64_t total = rows * cols;
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)p->sm_count * 16);
+  ec::fill_uniform_block_kernel<<<grid, 256, 0, p->stream>>>(seed, matrix_id, dst, rows, cols, ld_dst,
+                                                            row0, col0, global_ld);
+  EC_CUDA(cudaGetLastError());
+  p->launches++;
+  return EC_OK;
+}
 int ec_fill_uniform(ec_pipeline *p, uint64_t seed, uint64_t matrix_id, double *dst, int64_t count) {
   return ec_fill_uniform_batched(p, seed, matrix_id, dst, count, 1);
 }

@@ -162,6 +162,13 @@ int ec_fill_uniform(ec_pipeline *p, uint64_t seed, uint64_t matrix_id, double *d
 /* Same, `batch` matrices of `count` doubles each: matrix b gets matrix_id = first_id + b. */
 int ec_fill_uniform_batched(ec_pipeline *p, uint64_t seed, uint64_t first_id, double *dst,
                             int64_t count, int64_t batch);
+/* Same recipe for a rows x cols sub-block of a larger column-major matrix: element (i, j) of the
+ * block is the generator's value at global index (col0 + j) * global_ld + (row0 + i); written to
+ * dst with leading dimension ld_dst.  Lets every rank of the 2D-partitioned DGEMM synthesise its
+ * own blocks of the n = 65536 operands (34 GB each: too large for one host). */
+int ec_fill_uniform_block(ec_pipeline *p, uint64_t seed, uint64_t matrix_id, double *dst,
+                          int64_t rows, int64_t cols, int64_t ld_dst, int64_t row0, int64_t col0,
+                          int64_t global_ld);
 /* Launch counter: number of kernels this library has launched on this pipeline since creation. */
 int64_t ec_pipeline_launch_count(const ec_pipeline *p);
 /* Name of the kernel variant the last ec_dgemm* on this pipeline dispatched to. */

@@ -149,6 +149,15 @@ void oracle_fill_uniform(uint64_t seed, uint64_t matrix_id, double *dst, int64_t
   for (int64_t i = 0; i < count; ++i) dst[i] = oracle_uniform_at(seed, matrix_id, (uint64_t)i);
 }
 
+/* `count` generator values at indices start, start+stride, ...: one row or one column of a large
+ * synthetic matrix without materialising it (sampled verification of the n = 65536 product). */
+void oracle_fill_uniform_strided(uint64_t seed, uint64_t matrix_id, uint64_t start, uint64_t stride,
+                                 double *dst, int64_t count) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < count; ++i)
+    dst[i] = oracle_uniform_at(seed, matrix_id, start + (uint64_t)i * stride);
+}
+
 /* ---- comparison ------------------------------------------------------------------------------- */
 /* ||a-b||_F / min(||a||_F, ||b||_F): Eigen's isApprox(a,b,p) is exactly (this <= p), p = 1e-12
  * by default for double (src/tests/test_dot.cc:31,50,87-89 use the default). */

@@ -40,6 +40,8 @@ def lib():
         L.oracle_gemm_shape_check.argtypes = [i64, i64, i64, i64]
         L.oracle_fill_uniform.restype = None
         L.oracle_fill_uniform.argtypes = [u64, u64, vp, i64]
+        L.oracle_fill_uniform_strided.restype = None
+        L.oracle_fill_uniform_strided.argtypes = [u64, u64, u64, u64, vp, i64]
         L.oracle_uniform_at.restype = dbl
         L.oracle_uniform_at.argtypes = [u64, u64, u64]
         L.oracle_rel_frobenius.restype = dbl
@@ -109,6 +111,12 @@ def tensor_stream(kind, F, tensor, flavour="plain"):
 def fill_uniform(seed, matrix_id, shape):
     out = np.empty(shape, dtype=np.float64, order="F")
     lib().oracle_fill_uniform(seed, matrix_id, out.ctypes.data, out.size)
+    return out
+
+
+def uniform_strided(seed, matrix_id, start, stride, count):
+    out = np.empty(count, dtype=np.float64)
+    lib().oracle_fill_uniform_strided(seed, matrix_id, start, stride, out.ctypes.data, count)
     return out
 
 

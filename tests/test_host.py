@@ -87,3 +87,70 @@ def test_two_rank_gloo_shard_and_broadcast(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "GLOO_OK [6, 5]" in res.stdout or "GLOO_OK [5, 6]" in res.stdout, res.stdout
+
+
+SUMMA_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r})
+    import numpy as np, torch, torch.distributed as dist
+    from eigencuda_b200 import summa
+    from oracle import oracle_py as orc
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    m, n, k = 45, 38, 52                      # ragged on purpose: nothing divides evenly
+    L = summa.Layout(m, n, k, world, rank)
+    rg, cg = summa.make_groups(L)
+    A = orc.fill_uniform(orc.SEED, 0, (m, k)); B = orc.fill_uniform(orc.SEED, 1, (k, n))
+    # local blocks as (cols, rows) row-major views == column-major storage
+    A_loc = torch.from_numpy(np.ascontiguousarray(A[L.m0:L.m1, L.ka0:L.ka1].T))
+    B_loc = torch.from_numpy(np.ascontiguousarray(B[L.kb0:L.kb1, L.n0:L.n1].T))
+    C_loc = torch.full((L.c_shape[1], L.c_shape[0]), float("nan"), dtype=torch.float64)
+
+    def local_gemm(mm, nn, kk, At, lda, Bt, ldb, beta, Ct, ldc):
+        # the CPU oracle stands in for the GPU kernel in this host-logic test
+        Am = At.numpy().reshape(-1)[: lda * kk].reshape(kk, lda).T[:mm]
+        Bm = Bt.numpy().reshape(-1)[: ldb * nn].reshape(nn, ldb).T[:kk]
+        Cm = Ct.numpy().T
+        Cm[:] = orc.dgemm(Am, Bm, beta=beta, Cin=(Cm if beta != 0 else None))
+
+    summa.summa(L, A_loc, B_loc, C_loc, local_gemm, kb=7, row_group=rg, col_group=cg)
+    want = (A @ B)[L.m0:L.m1, L.n0:L.n1]
+    err = orc.rel_frobenius(C_loc.numpy().T, want)
+    assert err <= 1e-13, (rank, err)
+    ok = torch.tensor([1.0])
+    dist.all_reduce(ok)
+    if rank == 0:
+        print("SUMMA_OK", world, (L.P, L.Q), int(ok.item()))
+    dist.destroy_process_group()
+""")
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_summa_partition_gloo(tmp_path, world):
+    """The 2D block partition + panel broadcast logic (BASELINE.json configs[4]) on CPU ranks."""
+    script = tmp_path / "summa_worker.py"
+    script.write_text(SUMMA_WORKER.format(root=ROOT))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=280, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert f"SUMMA_OK {world}" in res.stdout, res.stdout
+
+
+def test_summa_layout_covers_everything():
+    from eigencuda_b200 import summa
+    for world in (1, 2, 4, 8):
+        m, n, k = 1000, 777, 555
+        seenC = np.zeros((m, n), dtype=int)
+        for r in range(world):
+            L = summa.Layout(m, n, k, world, r)
+            seenC[L.m0:L.m1, L.n0:L.n1] += 1
+            pan = L.panels(64)
+            assert pan[0][0] == 0 and pan[-1][1] == k and all(a[1] == b[0] for a, b in zip(pan, pan[1:]))
+            for k0, k1 in pan:       # a panel never straddles an ownership boundary
+                q, lo = L.a_owner_col(k0); assert lo <= k0 and k1 <= summa.block_range(k, L.Q, q)[1]
+                p, lo = L.b_owner_row(k0); assert lo <= k0 and k1 <= summa.block_range(k, L.P, p)[1]
+        assert (seenC == 1).all()
