@@ -2,7 +2,7 @@
 NCCL panel broadcasts (eigencuda_b200/summa.py).  Launch with torchrun, one rank per GPU:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \\
-        --master-port 29533 tools/summa_run.py --n 65536 --kb 2048
+        --master-port 29533 tools/summa_run.py --size 65536 --panel 2048
 
 Operands are generated on the device per owner block (34 GB per matrix at n = 65536).  Timing:
 CUDA events around the whole SUMMA loop, barrier on both sides, max over ranks.  Verification:
@@ -24,8 +24,8 @@ from eigencuda_b200 import summa
 
 SEED = 20200210
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=16384)
-ap.add_argument("--kb", type=int, default=2048)
+ap.add_argument("--size", type=int, default=16384, dest="n")
+ap.add_argument("--panel", type=int, default=2048, dest="kb")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--samples", type=int, default=6)
 args = ap.parse_args()
