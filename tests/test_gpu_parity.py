@@ -372,6 +372,21 @@ def test_fill_uniform_matches_oracle_bit_for_bit(pipe):
     assert d1.to_eigen()[0, 0] == float.fromhex(e["hex"])
 
 
+def test_fill_uniform_block_matches_global_generator(pipe):
+    """Sub-blocks generated by global index (2D-partitioned DGEMM operands) are bit-identical to
+    the corresponding window of the whole matrix from the CPU generator."""
+    gl_rows, gl_cols = 300, 200
+    whole = orc.fill_uniform(orc.SEED, 9, (gl_rows, gl_cols))
+    r0, c0, rows, cols, ld = 37, 50, 120, 64, 128
+    d = ec.CudaMatrix(np.zeros((ld, cols), order="F"), pipe.get_stream())
+    pipe.fill_uniform_block(orc.SEED, 9, d.data(), rows, cols, ld, r0, c0, gl_rows)
+    got = d.to_eigen()
+    assert np.array_equal(got[:rows], whole[r0:r0 + rows, c0:c0 + cols])
+    assert np.array_equal(got[rows:], np.zeros((ld - rows, cols)))
+    row = orc.uniform_strided(orc.SEED, 9, r0, gl_rows, gl_cols)
+    assert np.array_equal(row, whole[r0, :])
+
+
 # ---------------------------------------------------------------------------------------------
 # tensor stream: every kind, pageable (staged) and pinned (direct DMA) host memory
 # ---------------------------------------------------------------------------------------------
