@@ -199,6 +199,14 @@ class CudaPipeline:
         check(lib.ec_fill_uniform_block(self._h, seed, matrix_id, int(dst), rows, cols, ld_dst, row0,
                                         col0, global_ld))
 
+    def set_backend(self, backend):
+        """EC_BACKEND_FP64_DMMA (native, default) or EC_BACKEND_OZAKI_I8 (int8 tensor-core emulation
+        with the looser bound stated in DESIGN.md)."""
+        check(lib.ec_pipeline_set_backend(self._h, int(backend)))
+
+    def get_backend(self):
+        return int(lib.ec_pipeline_get_backend(self._h))
+
     def launch_count(self):
         return int(lib.ec_pipeline_launch_count(self._h))
 

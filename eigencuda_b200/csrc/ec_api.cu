@@ -23,6 +23,7 @@
 
 #include "../../include/eigencuda_b200.h"
 #include "dgemm_kernels.cuh"
+#include "ozaki_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -221,6 +222,10 @@ struct ec_pipeline {
   unsigned *sk_flags = nullptr;
   unsigned sk_epoch = 0;
   int stream_k = 1;   // 0 disables the stream-K schedule (EC_STREAM_K=0)
+  // EC_BACKEND_OZAKI_I8 workspace: digit planes and row/column scales, grown on demand
+  int8_t *oz_planes_a = nullptr, *oz_planes_b = nullptr;
+  double *oz_scale_a = nullptr, *oz_scale_b = nullptr;
+  size_t oz_planes_a_bytes = 0, oz_planes_b_bytes = 0, oz_scale_a_bytes = 0, oz_scale_b_bytes = 0;
 };
 
 struct ec_matrix {
@@ -453,6 +458,124 @@ TileChoice choose_tile(const ec_pipeline *p, int64_t m, int64_t n, int64_t k, in
   return pick;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// EC_BACKEND_OZAKI_I8: FP64 product emulated on the int8 tensor cores (ozaki_kernels.cuh)
+// ------------------------------------------------------------------------------------------
+constexpr int OZ_S = 7;   // digit planes: 49 fractional bits below each row/column maximum
+
+// Shapes the emulation takes; everything else runs the native FP64 kernels (which are at least
+// as accurate).  K <= 65536 keeps the int32 accumulators exact for 7 planes.
+bool ozaki_eligible(int64_t m, int64_t n, int64_t k) {
+  return k >= 64 && k <= 65536 && m >= 64 && n >= 32 && m * n * k >= (int64_t)128 * 128 * 128 &&
+         m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31);
+}
+
+template <class T>
+int oz_grow(T **buf, size_t *have, size_t want) {
+  if (want <= *have) return EC_OK;
+  if (*buf) EC_CUDA(cudaFree(*buf));
+  *buf = nullptr;
+  *have = 0;
+  EC_CUDA(cudaMalloc((void **)buf, want));
+  *have = want;
+  return EC_OK;
+}
+
+int oz_tensor_map(CUtensorMap *tm, const int8_t *planes, int64_t K, int64_t Kp, int64_t R, int64_t batch,
+                  int box_rows) {
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return fail(EC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)R, (cuuint64_t)OZ_S, (cuuint64_t)std::max<int64_t>(batch, 1)};
+  cuuint64_t strides[3] = {(cuuint64_t)Kp, (cuuint64_t)(R * Kp), (cuuint64_t)(OZ_S * R * Kp)};
+  cuuint32_t box[4] = {(cuuint32_t)ec::oz::OBK, (cuuint32_t)box_rows, (cuuint32_t)OZ_S, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)planes, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EC_ERR_CUDA, "cuTensorMapEncodeTiled (int8 planes) failed with CUresult %d", (int)r);
+  return EC_OK;
+}
+
+// Scale + split one operand: op(X) viewed as R rows x K, element (r, q) at X[r*rs + q*ks].
+int oz_split(ec_pipeline *p, const double *X, int64_t rs, int64_t ks, int64_t bstride, int64_t R, int64_t K,
+             int64_t Kp, int64_t batch, int8_t *planes, double *scale) {
+  ec::oz::SplitParams sp{X, rs, ks, bstride, R, K, Kp, batch, planes, scale};
+  const bool row_contig = (rs == 1 && ks != 1);
+  const int64_t rows = R * batch;
+  if (row_contig) {
+    const int grid = (int)std::min<int64_t>((rows + 127) / 128, (int64_t)p->sm_count * 16);
+    ec::oz::ozaki_rowscale_kernel<true><<<grid, 128, 0, p->stream>>>(sp);
+  } else {
+    const int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)p->sm_count * 16);
+    ec::oz::ozaki_rowscale_kernel<false><<<grid, 256, 0, p->stream>>>(sp);
+  }
+  EC_CUDA(cudaGetLastError());
+  const int64_t tiles = ((Kp + ec::oz::SPLIT_K - 1) / ec::oz::SPLIT_K) * ((R + ec::oz::SPLIT_ROWS - 1) / ec::oz::SPLIT_ROWS) * batch;
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)p->sm_count * 8);
+  if (row_contig)
+    ec::oz::ozaki_split_kernel<OZ_S, true><<<grid, ec::oz::SPLIT_THREADS, 0, p->stream>>>(sp);
+  else
+    ec::oz::ozaki_split_kernel<OZ_S, false><<<grid, ec::oz::SPLIT_THREADS, 0, p->stream>>>(sp);
+  EC_CUDA(cudaGetLastError());
+  p->launches += 2;
+  return EC_OK;
+}
+
+int ozaki_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha,
+                   const double *A, int64_t lda, int64_t stride_a, const double *B, int64_t ldb, int64_t stride_b,
+                   double beta, double *C, int64_t ldc, int64_t stride_c, int64_t batch) {
+  using Cfg = ec::oz::OzCfg<OZ_S>;
+  const int64_t Kp = (k + 15) / 16 * 16;
+  const bool a_batched = batch > 1 && stride_a != 0, b_batched = batch > 1 && stride_b != 0;
+  // chunk the batch so that the digit planes of a chunk stay around L2 size
+  const int64_t per_problem = OZ_S * Kp * ((a_batched ? m : 0) + (b_batched ? n : 0));
+  int64_t chunk = batch;
+  if (per_problem > 0) chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t)96 << 20) / per_problem));
+  if (const char *e = getenv("EC_OZAKI_CHUNK")) chunk = std::max<int64_t>(1, std::min<int64_t>(batch, atoll(e)));
+  const int64_t ca = a_batched ? chunk : 1, cb = b_batched ? chunk : 1;
+  int rc;
+  if ((rc = oz_grow(&p->oz_planes_a, &p->oz_planes_a_bytes, (size_t)(OZ_S * m * Kp * ca)))) return rc;
+  if ((rc = oz_grow(&p->oz_planes_b, &p->oz_planes_b_bytes, (size_t)(OZ_S * n * Kp * cb)))) return rc;
+  if ((rc = oz_grow(&p->oz_scale_a, &p->oz_scale_a_bytes, (size_t)(m * ca * 8)))) return rc;
+  if ((rc = oz_grow(&p->oz_scale_b, &p->oz_scale_b_bytes, (size_t)(n * cb * 8)))) return rc;
+  auto kern = ec::oz::ozaki_gemm_kernel<OZ_S>;
+  static std::atomic<uint64_t> configured{0};
+  const uint64_t bit = 1ull << (p->device & 63);
+  if (!(configured.load() & bit)) {
+    EC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured.fetch_or(bit);
+  }
+  // op(A)(r, q): N -> A[r + q*lda]; T -> A[r*lda + q].  op(B)^T(j, q) = op(B)(q, j): N -> B[j*ldb + q]; T -> B[q*ldb + j]
+  const int64_t a_rs = transa ? lda : 1, a_ks = transa ? 1 : lda;
+  const int64_t b_rs = transb ? 1 : ldb, b_ks = transb ? ldb : 1;
+  if (!a_batched && (rc = oz_split(p, A, a_rs, a_ks, 0, m, k, Kp, 1, p->oz_planes_a, p->oz_scale_a))) return rc;
+  if (!b_batched && (rc = oz_split(p, B, b_rs, b_ks, 0, n, k, Kp, 1, p->oz_planes_b, p->oz_scale_b))) return rc;
+  for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
+    const int64_t nb = std::min(chunk, batch - b0);
+    if (a_batched && (rc = oz_split(p, A + b0 * stride_a, a_rs, a_ks, stride_a, m, k, Kp, nb, p->oz_planes_a, p->oz_scale_a))) return rc;
+    if (b_batched && (rc = oz_split(p, B + b0 * stride_b, b_rs, b_ks, stride_b, n, k, Kp, nb, p->oz_planes_b, p->oz_scale_b))) return rc;
+    CUtensorMap tmA, tmB;
+    if ((rc = oz_tensor_map(&tmA, p->oz_planes_a, k, Kp, m, a_batched ? nb : 1, ec::oz::OM))) return rc;
+    if ((rc = oz_tensor_map(&tmB, p->oz_planes_b, k, Kp, n, b_batched ? nb : 1, ec::oz::ON))) return rc;
+    ec::oz::GemmOzParams gp;
+    gp.M = m; gp.N = n; gp.K = k; gp.batch = nb;
+    gp.alpha = alpha; gp.beta = beta;
+    gp.C = C + b0 * stride_c; gp.ldc = ldc; gp.stride_c = stride_c;
+    gp.sa = p->oz_scale_a; gp.sb = p->oz_scale_b;
+    gp.a_batched = a_batched; gp.b_batched = b_batched;
+    gp.tiles_m = (int)((m + ec::oz::OM - 1) / ec::oz::OM);
+    gp.tiles_n = (int)((n + ec::oz::ON - 1) / ec::oz::ON);
+    gp.total_tiles = (int64_t)gp.tiles_m * gp.tiles_n * nb;
+    const int grid = (int)std::min<int64_t>(gp.total_tiles, p->sm_count);
+    kern<<<grid, ec::oz::OTHREADS, Cfg::SMEM_BYTES, p->stream>>>(tmA, tmB, gp);
+    EC_CUDA(cudaGetLastError());
+    p->launches++;
+  }
+  p->last_kernel = "ozaki_i8_s7";
+  return EC_OK;
+}
+
 int dgemm_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n, int64_t k,
                    double alpha, const double *A, int64_t lda, int64_t stride_a, const double *B,
                    int64_t ldb, int64_t stride_b, double beta, double *C, int64_t ldc,
@@ -461,8 +584,6 @@ int dgemm_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
   if (m < 0 || n < 0 || k < 0 || batch < 0) return fail(EC_ERR_ARG, "negative dimension");
   if ((transa != EC_OP_N && transa != EC_OP_T) || (transb != EC_OP_N && transb != EC_OP_T))
     return fail(EC_ERR_ARG, "bad transpose flag");
-  if (p->backend != EC_BACKEND_FP64_DMMA)
-    return fail(EC_ERR_UNSUPPORTED, "backend %d is not built in this version", p->backend);
   if (m == 0 || n == 0 || batch == 0) return EC_OK;
   const int64_t a_rows = transa ? k : m, b_rows = transb ? n : k;
   if (lda < std::max<int64_t>(1, a_rows) || ldb < std::max<int64_t>(1, b_rows) ||
@@ -479,6 +600,12 @@ int dgemm_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
     p->launches++;
     p->last_kernel = "scale";
     return EC_OK;
+  }
+
+  if (p->backend == EC_BACKEND_OZAKI_I8 && ozaki_eligible(m, n, k)) {
+    const int rc = ozaki_dispatch(p, transa, transb, m, n, k, alpha, A, lda, stride_a, B, ldb, stride_b, beta,
+                                  C, ldc, stride_c, batch);
+    return rc;
   }
 
   Operand oa{A, lda, stride_a, transa == EC_OP_T, m, k};
@@ -803,6 +930,10 @@ int ec_pipeline_destroy(ec_pipeline *p) {
   p->staging.destroy();
   if (p->sk_workspace) cudaFree(p->sk_workspace);
   if (p->sk_flags) cudaFree(p->sk_flags);
+  if (p->oz_planes_a) cudaFree(p->oz_planes_a);
+  if (p->oz_planes_b) cudaFree(p->oz_planes_b);
+  if (p->oz_scale_a) cudaFree(p->oz_scale_a);
+  if (p->oz_scale_b) cudaFree(p->oz_scale_b);
   if (p->owns_stream) cudaStreamDestroy(p->stream);
   delete p;
   return EC_OK;
@@ -820,8 +951,8 @@ int ec_pipeline_synchronize(ec_pipeline *p) {
 
 int ec_pipeline_set_backend(ec_pipeline *p, int backend) {
   if (!p) return fail(EC_ERR_ARG, "null pipeline");
-  if (backend != EC_BACKEND_FP64_DMMA)
-    return fail(EC_ERR_UNSUPPORTED, "backend %d is not built in this version", backend);
+  if (backend != EC_BACKEND_FP64_DMMA && backend != EC_BACKEND_OZAKI_I8)
+    return fail(EC_ERR_UNSUPPORTED, "unknown backend %d", backend);
   p->backend = backend;
   return EC_OK;
 }

@@ -512,3 +512,83 @@ def test_full_size_transposed_1000(pipe):
         assert orc.rel_frobenius(got, orc.cpu_product(F.T, t)) <= TOL
     for got, t in zip(pipe.basis_transform(F, ts), ts):
         assert orc.rel_frobenius(got, orc.cpu_product(orc.cpu_product(F.T, t), F)) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# EC_BACKEND_OZAKI_I8: the selectable int8 tensor-core emulation, with its stated (looser) bound
+# ---------------------------------------------------------------------------------------------
+OZ_TOL = 1e-12   # same bar as the native path on well-scaled data (measured ~5e-15)
+
+
+@pytest.fixture()
+def ozaki(pipe):
+    pipe.set_backend(ec.EC_BACKEND_OZAKI_I8)
+    yield pipe
+    pipe.set_backend(ec.EC_BACKEND_FP64_DMMA)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("shape", [(256, 192, 320), (200, 136, 520), (130, 70, 1000), (512, 512, 512), (384, 100, 72)])
+def test_ozaki_backend_all_layouts(ozaki, ta, tb, shape):
+    m, n, k = shape
+    got, want = run_dgemm(ozaki, ta, tb, m, n, k, 1.25, -0.5, lda_pad=2, ldb_pad=4, ldc_pad=2, seed=m + k)
+    assert ozaki.last_kernel() == "ozaki_i8_s7"
+    assert orc.rel_frobenius(got, want) <= OZ_TOL
+
+
+def test_ozaki_small_shapes_fall_back_to_native(ozaki):
+    got, want = run_dgemm(ozaki, False, False, 48, 40, 32, 1.0, 0.0, seed=3)
+    assert not ozaki.last_kernel().startswith("ozaki")
+    assert orc.rel_frobenius(got, want) <= TOL
+
+
+def test_ozaki_stated_bound_on_badly_scaled_rows(ozaki):
+    """The emulation's bound is norm-wise per row of A and per column of B:
+    |E_ij| <= (S+2) * K * 128^-S * 2^Ei * 2^Ej with 2^Ei <= 4 * max_p |a_ip| (S = 7).  Rows whose
+    entries span 16 orders of magnitude lose their small entries -- by design -- but stay inside
+    that bound; the native path is the one to use when that matters."""
+    rng = np.random.default_rng(5)
+    m, n, k = 256, 128, 384
+    A = np.asfortranarray(rng.uniform(-1, 1, (m, k)) * 10.0 ** rng.integers(-8, 9, (m, k)))
+    B = np.asfortranarray(rng.uniform(-1, 1, (k, n)) * 10.0 ** rng.integers(-8, 9, (k, n)))
+    dA, dB = ec.CudaMatrix(A, ozaki.get_stream()), ec.CudaMatrix(B, ozaki.get_stream())
+    dC = ec.CudaMatrix(m, n, ozaki.get_stream())
+    ozaki.gemm(dA, dB, dC)
+    assert ozaki.last_kernel() == "ozaki_i8_s7"
+    got = dC.to_eigen()
+    want = orc.dgemm(A, B, flavour="ld")
+    bound = 9 * k * 128.0 ** -7 * np.outer(4 * np.abs(A).max(axis=1), 4 * np.abs(B).max(axis=0))
+    assert (np.abs(got - want) <= bound).all()
+    # and row/column scaling by powers of two is exact: scaling inputs scales outputs bit for bit
+    dA2 = ec.CudaMatrix(A * 2.0 ** 40, ozaki.get_stream())
+    ozaki.gemm(dA2, dB, dC)
+    assert np.array_equal(dC.to_eigen(), got * 2.0 ** 40)
+
+
+def test_ozaki_nan_and_zero_rows(ozaki):
+    m, n, k = 256, 128, 256
+    A, B = rnd(1, (m, k)), rnd(2, (k, n))
+    A[7, :] = 0.0
+    A[9, 100] = np.nan
+    B[3, 5] = np.inf
+    dA, dB = ec.CudaMatrix(A, ozaki.get_stream()), ec.CudaMatrix(B, ozaki.get_stream())
+    dC = ec.CudaMatrix(m, n, ozaki.get_stream())
+    ozaki.gemm(dA, dB, dC)
+    got = dC.to_eigen()
+    assert np.array_equal(got[7, np.arange(n) != 5], np.zeros(n - 1))     # zero row -> exact zeros
+    assert np.isnan(got[9, :]).all() and np.isnan(got[:, 5]).all()       # non-finite input poisons its row / column
+    ok = np.ones((m, n), bool); ok[9, :] = False; ok[:, 5] = False
+    want = orc.dgemm(np.where(np.isfinite(A), A, 0), np.where(np.isfinite(B), B, 0), flavour="ld")
+    assert orc.rel_frobenius(np.where(ok, got, 0), np.where(ok, want, 0)) <= OZ_TOL
+
+
+def test_ozaki_tensor_stream_and_batch_chunking(ozaki, monkeypatch):
+    monkeypatch.setenv("EC_OZAKI_CHUNK", "5")          # 23 matrices -> 5 chunks, ragged tail
+    n, count = 192, 23
+    F = orc.fill_uniform(orc.SEED, 0, (n, n))
+    ts = [orc.fill_uniform(orc.SEED, i + 1, (n, n)) for i in range(count)]
+    for kind, name in ((ec.EC_STREAM_RIGHT, "right"), (ec.EC_STREAM_LEFT_T, "left_t"), (ec.EC_STREAM_BASIS, "basis")):
+        res = ozaki.tensor_stream(kind, F, ts)
+        for r, w in zip(res, orc.tensor_stream(name, F, ts, flavour="fast")):
+            assert orc.rel_frobenius(r, w) <= OZ_TOL
+    assert ozaki.last_kernel() == "ozaki_i8_s7"
