@@ -225,7 +225,8 @@ struct ec_pipeline {
   // EC_BACKEND_OZAKI_I8 workspace: digit planes and row/column scales, grown on demand
   int8_t *oz_planes_a = nullptr, *oz_planes_b = nullptr;
   double *oz_scale_a = nullptr, *oz_scale_b = nullptr;
-  size_t oz_planes_a_bytes = 0, oz_planes_b_bytes = 0, oz_scale_a_bytes = 0, oz_scale_b_bytes = 0;
+  unsigned long long *oz_amax = nullptr;
+  size_t oz_planes_a_bytes = 0, oz_planes_b_bytes = 0, oz_scale_a_bytes = 0, oz_scale_b_bytes = 0, oz_amax_bytes = 0;
 };
 
 struct ec_matrix {
@@ -498,25 +499,24 @@ int oz_tensor_map(CUtensorMap *tm, const int8_t *planes, int64_t K, int64_t Kp, 
 }
 
 // Scale + split one operand: op(X) viewed as R rows x K, element (r, q) at X[r*rs + q*ks].
+// `amax` is scratch for R*batch abs-max bit patterns.
 int oz_split(ec_pipeline *p, const double *X, int64_t rs, int64_t ks, int64_t bstride, int64_t R, int64_t K,
-             int64_t Kp, int64_t batch, int8_t *planes, double *scale) {
+             int64_t Kp, int64_t batch, int8_t *planes, double *scale, unsigned long long *amax) {
   ec::oz::SplitParams sp{X, rs, ks, bstride, R, K, Kp, batch, planes, scale};
   const bool row_contig = (rs == 1 && ks != 1);
-  const int64_t rows = R * batch;
+  EC_CUDA(cudaMemsetAsync(amax, 0, (size_t)(R * batch) * 8, p->stream));
+  const int64_t rt = (R + ec::oz::SPLIT_ROWS - 1) / ec::oz::SPLIT_ROWS;
+  const int64_t tiles_k = ((K + ec::oz::SPLIT_K - 1) / ec::oz::SPLIT_K) * rt * batch;
+  const int64_t tiles_kp = ((Kp + ec::oz::SPLIT_K - 1) / ec::oz::SPLIT_K) * rt * batch;
+  const int g1 = (int)std::min<int64_t>(tiles_k, (int64_t)p->sm_count * 8);
+  const int g2 = (int)std::min<int64_t>(tiles_kp, (int64_t)p->sm_count * 8);
   if (row_contig) {
-    const int grid = (int)std::min<int64_t>((rows + 127) / 128, (int64_t)p->sm_count * 16);
-    ec::oz::ozaki_rowscale_kernel<true><<<grid, 128, 0, p->stream>>>(sp);
+    ec::oz::ozaki_absmax_kernel<true><<<g1, ec::oz::SPLIT_THREADS, 0, p->stream>>>(sp, amax);
+    ec::oz::ozaki_split_kernel<OZ_S, true><<<g2, ec::oz::SPLIT_THREADS, 0, p->stream>>>(sp, amax);
   } else {
-    const int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)p->sm_count * 16);
-    ec::oz::ozaki_rowscale_kernel<false><<<grid, 256, 0, p->stream>>>(sp);
+    ec::oz::ozaki_absmax_kernel<false><<<g1, ec::oz::SPLIT_THREADS, 0, p->stream>>>(sp, amax);
+    ec::oz::ozaki_split_kernel<OZ_S, false><<<g2, ec::oz::SPLIT_THREADS, 0, p->stream>>>(sp, amax);
   }
-  EC_CUDA(cudaGetLastError());
-  const int64_t tiles = ((Kp + ec::oz::SPLIT_K - 1) / ec::oz::SPLIT_K) * ((R + ec::oz::SPLIT_ROWS - 1) / ec::oz::SPLIT_ROWS) * batch;
-  const int grid = (int)std::min<int64_t>(tiles, (int64_t)p->sm_count * 8);
-  if (row_contig)
-    ec::oz::ozaki_split_kernel<OZ_S, true><<<grid, ec::oz::SPLIT_THREADS, 0, p->stream>>>(sp);
-  else
-    ec::oz::ozaki_split_kernel<OZ_S, false><<<grid, ec::oz::SPLIT_THREADS, 0, p->stream>>>(sp);
   EC_CUDA(cudaGetLastError());
   p->launches += 2;
   return EC_OK;
@@ -539,6 +539,7 @@ int ozaki_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
   if ((rc = oz_grow(&p->oz_planes_b, &p->oz_planes_b_bytes, (size_t)(OZ_S * n * Kp * cb)))) return rc;
   if ((rc = oz_grow(&p->oz_scale_a, &p->oz_scale_a_bytes, (size_t)(m * ca * 8)))) return rc;
   if ((rc = oz_grow(&p->oz_scale_b, &p->oz_scale_b_bytes, (size_t)(n * cb * 8)))) return rc;
+  if ((rc = oz_grow(&p->oz_amax, &p->oz_amax_bytes, (size_t)(std::max(m * ca, n * cb) * 8)))) return rc;
   auto kern = ec::oz::ozaki_gemm_kernel<OZ_S>;
   static std::atomic<uint64_t> configured{0};
   const uint64_t bit = 1ull << (p->device & 63);
@@ -549,12 +550,12 @@ int ozaki_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
   // op(A)(r, q): N -> A[r + q*lda]; T -> A[r*lda + q].  op(B)^T(j, q) = op(B)(q, j): N -> B[j*ldb + q]; T -> B[q*ldb + j]
   const int64_t a_rs = transa ? lda : 1, a_ks = transa ? 1 : lda;
   const int64_t b_rs = transb ? 1 : ldb, b_ks = transb ? ldb : 1;
-  if (!a_batched && (rc = oz_split(p, A, a_rs, a_ks, 0, m, k, Kp, 1, p->oz_planes_a, p->oz_scale_a))) return rc;
-  if (!b_batched && (rc = oz_split(p, B, b_rs, b_ks, 0, n, k, Kp, 1, p->oz_planes_b, p->oz_scale_b))) return rc;
+  if (!a_batched && (rc = oz_split(p, A, a_rs, a_ks, 0, m, k, Kp, 1, p->oz_planes_a, p->oz_scale_a, p->oz_amax))) return rc;
+  if (!b_batched && (rc = oz_split(p, B, b_rs, b_ks, 0, n, k, Kp, 1, p->oz_planes_b, p->oz_scale_b, p->oz_amax))) return rc;
   for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
     const int64_t nb = std::min(chunk, batch - b0);
-    if (a_batched && (rc = oz_split(p, A + b0 * stride_a, a_rs, a_ks, stride_a, m, k, Kp, nb, p->oz_planes_a, p->oz_scale_a))) return rc;
-    if (b_batched && (rc = oz_split(p, B + b0 * stride_b, b_rs, b_ks, stride_b, n, k, Kp, nb, p->oz_planes_b, p->oz_scale_b))) return rc;
+    if (a_batched && (rc = oz_split(p, A + b0 * stride_a, a_rs, a_ks, stride_a, m, k, Kp, nb, p->oz_planes_a, p->oz_scale_a, p->oz_amax))) return rc;
+    if (b_batched && (rc = oz_split(p, B + b0 * stride_b, b_rs, b_ks, stride_b, n, k, Kp, nb, p->oz_planes_b, p->oz_scale_b, p->oz_amax))) return rc;
     CUtensorMap tmA, tmB;
     if ((rc = oz_tensor_map(&tmA, p->oz_planes_a, k, Kp, m, a_batched ? nb : 1, ec::oz::OM))) return rc;
     if ((rc = oz_tensor_map(&tmB, p->oz_planes_b, k, Kp, n, b_batched ? nb : 1, ec::oz::ON))) return rc;
@@ -934,6 +935,7 @@ int ec_pipeline_destroy(ec_pipeline *p) {
   if (p->oz_planes_b) cudaFree(p->oz_planes_b);
   if (p->oz_scale_a) cudaFree(p->oz_scale_a);
   if (p->oz_scale_b) cudaFree(p->oz_scale_b);
+  if (p->oz_amax) cudaFree(p->oz_amax);
   if (p->owns_stream) cudaStreamDestroy(p->stream);
   delete p;
   return EC_OK;

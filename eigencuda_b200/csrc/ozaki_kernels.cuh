@@ -16,7 +16,7 @@
 // Non-finite inputs poison the row/column scale with NaN.  K <= 65536 per launch keeps int32
 // exact for S <= 7 (7 * 65536 * 4225 < 2^31).
 //
-//   ozaki_rowscale_kernel   per-row power-of-two scale (HBM-bound read)
+//   ozaki_absmax_kernel     per-row abs-max bits (atomicMax), coalesced for either operand layout
 //   ozaki_split_kernel      digits: x -> 128x -> rint via the 1.5*2^52 trick, all on the FP64
 //                           pipe, transposed through smem so that every plane is K-major
 //                           (what the UMMA shared-memory descriptor wants), 16-byte stores
@@ -52,63 +52,69 @@ struct SplitParams {
   double *scale;             // [batch][R], = 2^E
 };
 
-// One thread per row when rows are memory-contiguous (rs == 1), one warp per row otherwise.
+// Row abs-max as the bit pattern of |x| (non-negative doubles order like unsigned integers, and
+// Inf / NaN sort above every finite value, which is exactly the poisoning wanted).  Same 32 x 128
+// tiling as the split kernel: coalesced whichever way the operand is laid out, one atomicMax per
+// row per tile.  `amax` must be zeroed before the launch.
+constexpr int SPLIT_ROWS = 32, SPLIT_K = 128, SPLIT_THREADS = 256;
+constexpr int SPLIT_RS = 137, SPLIT_SS = 17;
+
 template <bool ROW_CONTIG>
-__global__ void ozaki_rowscale_kernel(const SplitParams p) {
-  const int64_t total = p.R * p.batch;
-  if (ROW_CONTIG) {
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t b = idx / p.R, r = idx - b * p.R;
-      const double *x = p.X + b * p.bstride + r * p.rs;
-      double amax = 0.0;
-      bool bad = false;
-      for (int64_t k = 0; k < p.K; ++k) {
-        const double v = fabs(x[k * p.ks]);
-        bad |= !(v <= 1.7976931348623157e308);
-        amax = fmax(amax, v);
+__global__ void __launch_bounds__(SPLIT_THREADS) ozaki_absmax_kernel(const SplitParams p, unsigned long long *amax) {
+  __shared__ unsigned long long red[SPLIT_THREADS];
+  const int64_t ktiles = (p.K + SPLIT_K - 1) / SPLIT_K, rtiles = (p.R + SPLIT_ROWS - 1) / SPLIT_ROWS;
+  const int64_t total = ktiles * rtiles * p.batch;
+  for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const int64_t b = t / (ktiles * rtiles);
+    const int64_t rem = t - b * ktiles * rtiles;
+    const int64_t r0 = (rem / ktiles) * SPLIT_ROWS, k0 = (rem % ktiles) * SPLIT_K;
+    const double *X = p.X + b * p.bstride;
+    // thread -> (row, k-lane): lanes run along the memory-contiguous direction
+    const int r = ROW_CONTIG ? (threadIdx.x & 31) : (threadIdx.x >> 3);
+    const int kl = ROW_CONTIG ? (threadIdx.x >> 5) : (threadIdx.x & 7);     // 8 k-lanes per row
+    unsigned long long m = 0ull;
+    if (r0 + r < p.R) {
+      const double *xr = X + (r0 + r) * p.rs;
+#pragma unroll 4
+      for (int i = 0; i < SPLIT_K / 8; ++i) {
+        // ROW_CONTIG: a warp reads 32 consecutive rows of one k; else 8 lanes read 8 consecutive k
+        const int64_t k = k0 + (ROW_CONTIG ? kl + 8 * i : kl + 8 * i);
+        if (k < p.K) {
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(xr[k * p.ks]));
+          m = bits > m ? bits : m;
+        }
       }
-      int e = ((__double2hiint(amax) >> 20) & 0x7ff) - 1022 + 1;   // |x| * 2^-e < 1/2
-      if (amax == 0.0) e = 0;
-      e = max(-1000, min(1000, e));
-      p.scale[idx] = bad ? __longlong_as_double(0x7ff8000000000000LL) : __hiloint2double((1023 + e) << 20, 0);
     }
-  } else {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t idx = warp; idx < total; idx += nwarps) {
-      const int64_t b = idx / p.R, r = idx - b * p.R;
-      const double *x = p.X + b * p.bstride + r * p.rs;
-      double amax = 0.0;
-      int bad = 0;
-      for (int64_t k = lane; k < p.K; k += 32) {
-        const double v = fabs(x[k * p.ks]);
-        bad |= !(v <= 1.7976931348623157e308);
-        amax = fmax(amax, v);
-      }
+    __syncthreads();
+    red[ROW_CONTIG ? (kl * 32 + r) : (r * 8 + kl)] = m;
+    __syncthreads();
+    if (threadIdx.x < SPLIT_ROWS) {
+      const int rr = threadIdx.x;
+      unsigned long long mm = 0ull;
 #pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+      for (int j = 0; j < 8; ++j) {
+        const unsigned long long v = red[ROW_CONTIG ? (j * 32 + rr) : (rr * 8 + j)];
+        mm = v > mm ? v : mm;
       }
-      if (lane == 0) {
-        int e = ((__double2hiint(amax) >> 20) & 0x7ff) - 1022 + 1;
-        if (amax == 0.0) e = 0;
-        e = max(-1000, min(1000, e));
-        p.scale[idx] = bad ? __longlong_as_double(0x7ff8000000000000LL) : __hiloint2double((1023 + e) << 20, 0);
-      }
+      if (r0 + rr < p.R && mm) atomicMax(amax + b * p.R + r0 + rr, mm);
     }
   }
 }
 
+// 2^E from the abs-max bits: |x| * 2^-E < 1/2 for every entry of the row; NaN when the row holds a
+// non-finite value; 1 for an all-zero row.
+__device__ __forceinline__ double scale_from_amax(unsigned long long bits) {
+  if (bits >= 0x7ff0000000000000ull) return __longlong_as_double(0x7ff8000000000000LL);
+  if (bits == 0ull) return 1.0;
+  int e = (int)((bits >> 52) & 0x7ff) - 1022 + 1;
+  e = max(-1000, min(1000, e));
+  return __hiloint2double((1023 + e) << 20, 0);
+}
+
 // Tile of 32 rows x 128 k per block of 256 threads; staged in smem (row stride 137, 16-element
 // segments at stride 17: conflict-free for both the coalesced fill and the per-thread reads).
-constexpr int SPLIT_ROWS = 32, SPLIT_K = 128, SPLIT_THREADS = 256;
-constexpr int SPLIT_RS = 137, SPLIT_SS = 17;
-
 template <int S, bool ROW_CONTIG>
-__global__ void __launch_bounds__(SPLIT_THREADS) ozaki_split_kernel(const SplitParams p) {
+__global__ void __launch_bounds__(SPLIT_THREADS) ozaki_split_kernel(const SplitParams p, const unsigned long long *amax) {
   __shared__ double tile[SPLIT_ROWS * SPLIT_RS];
   const int64_t ktiles = (p.Kp + SPLIT_K - 1) / SPLIT_K, rtiles = (p.R + SPLIT_ROWS - 1) / SPLIT_ROWS;
   const int64_t total = ktiles * rtiles * p.batch;
@@ -128,7 +134,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS) ozaki_split_kernel(const SplitP
     __syncthreads();
     const int row = threadIdx.x >> 3, seg = threadIdx.x & 7;
     if (r0 + row < p.R && k0 + seg * 16 < p.Kp) {
-      const double sc = p.scale[b * p.R + r0 + row];
+      const double sc = scale_from_amax(amax[b * p.R + r0 + row]);
+      if (k0 == 0 && seg == 0) p.scale[b * p.R + r0 + row] = sc;
       // 1 / 2^E, exact (a NaN scale makes everything NaN -> digits 0, the epilogue re-poisons)
       const double inv = __hiloint2double((2046 - ((__double2hiint(sc) >> 20) & 0x7ff)) << 20, 0);
       uint32_t w[S][4];
@@ -160,6 +167,18 @@ __global__ void __launch_bounds__(SPLIT_THREADS) ozaki_split_kernel(const SplitP
 // ---------------------------------------------------------------------------------------------
 // the int8 GEMM on the digit planes
 // ---------------------------------------------------------------------------------------------
+// Tile order: groups of RASTER_M m-tiles, inside a group m fastest then n, so that the ~148 tiles in
+// flight share few A row-panels AND few B column-panels (operand bytes per wave ~ sqrt-like instead
+// of all of A): at n = 8192 that is 7 GB instead of 26 GB of HBM reads per product.
+constexpr int RASTER_M = 8;
+__device__ __forceinline__ void oz_tile_coords(int r, int tiles_m, int tiles_n, int &tm, int &tn) {
+  const int per_group = RASTER_M * tiles_n;
+  const int grp = r / per_group, in = r - grp * per_group;
+  const int gm = min(RASTER_M, tiles_m - grp * RASTER_M);   // rows in this (possibly short) group
+  tm = grp * RASTER_M + in % gm;
+  tn = in / gm;
+}
+
 struct GemmOzParams {
   int64_t M, N, K, batch;
   double alpha, beta;
@@ -274,7 +293,9 @@ __global__ void __launch_bounds__(OTHREADS, 1)
       for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int b = (int)(tile / tiles_per_problem);
         const int r = (int)(tile - (int64_t)b * tiles_per_problem);
-        const int m0 = (r % p.tiles_m) * OM, n0 = (r / p.tiles_m) * ON;
+        int tm, tn;
+        oz_tile_coords(r, p.tiles_m, p.tiles_n, tm, tn);
+        const int m0 = tm * OM, n0 = tn * ON;
         const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
         for (int kc = 0; kc < nk; ++kc) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -289,7 +310,10 @@ __global__ void __launch_bounds__(OTHREADS, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ON >> 3) << 17) | ((uint32_t)(OM >> 4) << 24);
+      // s32 accumulate, signed 8-bit A and B, both K-major, M = 128, N in the descriptor per call
+      auto idesc_n = [](int n) -> uint32_t {
+        return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(OM >> 4) << 24);
+      };
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
       for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -299,16 +323,23 @@ __global__ void __launch_bounds__(OTHREADS, 1)
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sA = base + stage * Cfg::STAGE_BYTES, sB = sA + Cfg::A_BYTES;
+          // Plane s of A against planes t = 0..S-1-s of B.  Those B planes are contiguous in smem
+          // (one K-major matrix of 64*(S-s) rows) and their products belong to the accumulators
+          // d = s..S-1, which are contiguous in TMEM (columns 64*s ..), so ONE MMA of N up to 256
+          // does what would otherwise be up to four: 10 MMAs instead of 28 per 32-byte k-step, and
+          // the 128-row A tile is re-read from shared memory 10 times instead of 28 (the N = 64
+          // form needs 192 B/clk of operand bandwidth; shared memory delivers 128).
 #pragma unroll
-          for (int d = 0; d < S; ++d) {
+          for (int kk = 0; kk < OBK / 32; ++kk) {
 #pragma unroll
-            for (int s = 0; s <= d; ++s) {
-              const int t = d - s;
+            for (int s = 0; s < S; ++s) {
+              const uint64_t da = umma_desc_sw64(sA + s * (OM * OBK) + kk * 32);
+              constexpr int dummy = 0; (void)dummy;
 #pragma unroll
-              for (int kk = 0; kk < OBK / 32; ++kk) {
-                const uint64_t da = umma_desc_sw64(sA + s * (OM * OBK) + kk * 32);
-                const uint64_t db = umma_desc_sw64(sB + t * (ON * OBK) + kk * 32);
-                umma_i8(tmem + d * ON, da, db, idesc, (kc > 0 || s > 0 || kk > 0) ? 1u : 0u);
+              for (int c0 = 0; c0 < ON * (S - s); c0 += 256) {
+                const int nn = (ON * (S - s) - c0) < 256 ? (ON * (S - s) - c0) : 256;
+                const uint64_t db = umma_desc_sw64(sB + (c0 / ON) * (ON * OBK) + kk * 32);
+                umma_i8(tmem + s * ON + c0, da, db, idesc_n(nn), (kc > 0 || kk > 0 || s > 0) ? 1u : 0u);
               }
             }
           }
@@ -328,7 +359,9 @@ __global__ void __launch_bounds__(OTHREADS, 1)
     for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = (int)(tile / tiles_per_problem);
       const int r = (int)(tile - (int64_t)b * tiles_per_problem);
-      const int m0 = (r % p.tiles_m) * OM, n0 = (r / p.tiles_m) * ON;
+      int tm, tn;
+      oz_tile_coords(r, p.tiles_m, p.tiles_n, tm, tn);
+      const int m0 = tm * OM, n0 = tn * ON;
       // column scales of this tile (visible to all epilogue warps after the named barrier)
       asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's readers are done
       if (et < ON) {
