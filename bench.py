@@ -440,6 +440,54 @@ def main():
         pin_out4.close()
         del F4, T4, R4
         torch.cuda.empty_cache()
+        # the selectable EC_BACKEND_OZAKI_I8 path (int8 tcgen05 emulation, looser stated bound):
+        # the main workload resident in HBM, a few square sizes, and its measured error
+        oz = {"bound": "|E_ij| <= 9*K*128^-7 * 2^Ei * 2^Ej (row/column power-of-two scales), DESIGN.md section 3.4"}
+        pipe.set_backend(ec.EC_BACKEND_OZAKI_I8)
+        co = 2048
+        To = torch.empty(co * elems, dtype=torch.float64, device=dev)
+        Ro = torch.empty(co * elems, dtype=torch.float64, device=dev)
+        pipe.fill_uniform(SEED, 1, To.data_ptr(), elems, co)
+        run = lambda: pipe.tensor_stream_device(ec.EC_STREAM_RIGHT, F.data_ptr(), n, n, To.data_ptr(), Ro.data_ptr(), co, n, n)
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(3):
+            run()
+        b.record(stream)
+        b.synchronize()
+        ms = a.elapsed_time(b) / 3
+        Ri = Ro[5 * elems:6 * elems].cpu().numpy().reshape(n, n, order="F")
+        want = orc.dgemm(orc.fill_uniform(SEED, 6, (n, n)), orc.fill_uniform(SEED, 0, (n, n)), flavour="ld")
+        oz["tensor_stream_resident"] = {"matrices": co, "n": n, "ms_per_step": ms, "matrices_per_s": co / (ms * 1e-3),
+                                        "tflops_fp64_equivalent": co * flops_per_matrix / (ms * 1e-3) / 1e12,
+                                        "kernel": pipe.last_kernel(),
+                                        "rel_frobenius_vs_long_double": orc.rel_frobenius(Ri, want)}
+        del To, Ro
+        oz["dgemm"] = []
+        for nn in (2048, 4096, 8192):
+            A = torch.empty(nn * nn, dtype=torch.float64, device=dev)
+            B = torch.empty(nn * nn, dtype=torch.float64, device=dev)
+            Cm = torch.empty(nn * nn, dtype=torch.float64, device=dev)
+            pipe.fill_uniform(SEED, 0, A.data_ptr(), nn * nn, 1)
+            pipe.fill_uniform(SEED, 1, B.data_ptr(), nn * nn, 1)
+            for _ in range(2):
+                pipe.dgemm(0, 0, nn, nn, nn, 1.0, A.data_ptr(), nn, B.data_ptr(), nn, 0.0, Cm.data_ptr(), nn)
+            best = float("inf")
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                pipe.dgemm(0, 0, nn, nn, nn, 1.0, A.data_ptr(), nn, B.data_ptr(), nn, 0.0, Cm.data_ptr(), nn)
+                b.record(stream)
+                b.synchronize()
+                best = min(best, a.elapsed_time(b))
+            oz["dgemm"].append({"n": nn, "ms": best, "tflops_fp64_equivalent": 2.0 * nn ** 3 / (best * 1e-3) / 1e12})
+            del A, B, Cm
+        pipe.set_backend(ec.EC_BACKEND_FP64_DMMA)
+        extras["ozaki_i8"] = oz
+        torch.cuda.empty_cache()
         # the main workload from PAGEABLE host memory (what a std::vector<Eigen::MatrixXd> is):
         # staged through the engine's pinned ring by worker threads
         cp_ = 1024

@@ -227,6 +227,8 @@ struct ec_pipeline {
   double *oz_scale_a = nullptr, *oz_scale_b = nullptr;
   unsigned long long *oz_amax = nullptr;
   size_t oz_planes_a_bytes = 0, oz_planes_b_bytes = 0, oz_scale_a_bytes = 0, oz_scale_b_bytes = 0, oz_amax_bytes = 0;
+  cudaStream_t oz_split_stream = nullptr;          // splits of chunk c+1 overlap the GEMM of chunk c
+  cudaEvent_t oz_ev_split[2] = {nullptr, nullptr}, oz_ev_gemm[2] = {nullptr, nullptr};
 };
 
 struct ec_matrix {
@@ -528,18 +530,32 @@ int ozaki_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
   using Cfg = ec::oz::OzCfg<OZ_S>;
   const int64_t Kp = (k + 15) / 16 * 16;
   const bool a_batched = batch > 1 && stride_a != 0, b_batched = batch > 1 && stride_b != 0;
-  // chunk the batch so that the digit planes of a chunk stay around L2 size
+  // chunk the batch so that the digit planes of a chunk stay around L2 size; the batched
+  // operand(s) are double-buffered so that the split of chunk c+1 (LSU / FP64 pipe / HBM) runs on
+  // a side stream underneath the GEMM of chunk c (tensor cores / L2)
   const int64_t per_problem = OZ_S * Kp * ((a_batched ? m : 0) + (b_batched ? n : 0));
   int64_t chunk = batch;
-  if (per_problem > 0) chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t)96 << 20) / per_problem));
+  if (per_problem > 0) chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t)192 << 20) / per_problem));
   if (const char *e = getenv("EC_OZAKI_CHUNK")) chunk = std::max<int64_t>(1, std::min<int64_t>(batch, atoll(e)));
+  const int64_t nchunks = (batch + chunk - 1) / chunk;
+  const bool pipelined = nchunks > 1 && (a_batched || b_batched);
+  const int nbuf = pipelined ? 2 : 1;
   const int64_t ca = a_batched ? chunk : 1, cb = b_batched ? chunk : 1;
+  const size_t pa = (size_t)(OZ_S * m * Kp * ca), pb = (size_t)(OZ_S * n * Kp * cb);
+  const size_t sa_b = (size_t)(m * ca * 8), sb_b = (size_t)(n * cb * 8), am_b = (size_t)(std::max(m * ca, n * cb) * 8);
   int rc;
-  if ((rc = oz_grow(&p->oz_planes_a, &p->oz_planes_a_bytes, (size_t)(OZ_S * m * Kp * ca)))) return rc;
-  if ((rc = oz_grow(&p->oz_planes_b, &p->oz_planes_b_bytes, (size_t)(OZ_S * n * Kp * cb)))) return rc;
-  if ((rc = oz_grow(&p->oz_scale_a, &p->oz_scale_a_bytes, (size_t)(m * ca * 8)))) return rc;
-  if ((rc = oz_grow(&p->oz_scale_b, &p->oz_scale_b_bytes, (size_t)(n * cb * 8)))) return rc;
-  if ((rc = oz_grow(&p->oz_amax, &p->oz_amax_bytes, (size_t)(std::max(m * ca, n * cb) * 8)))) return rc;
+  if ((rc = oz_grow(&p->oz_planes_a, &p->oz_planes_a_bytes, pa * (a_batched ? nbuf : 1)))) return rc;
+  if ((rc = oz_grow(&p->oz_planes_b, &p->oz_planes_b_bytes, pb * (b_batched ? nbuf : 1)))) return rc;
+  if ((rc = oz_grow(&p->oz_scale_a, &p->oz_scale_a_bytes, sa_b * (a_batched ? nbuf : 1)))) return rc;
+  if ((rc = oz_grow(&p->oz_scale_b, &p->oz_scale_b_bytes, sb_b * (b_batched ? nbuf : 1)))) return rc;
+  if ((rc = oz_grow(&p->oz_amax, &p->oz_amax_bytes, am_b * 3))) return rc;   // [shared operand, buffer 0, buffer 1]
+  if (pipelined && !p->oz_split_stream) {
+    EC_CUDA(cudaStreamCreateWithFlags(&p->oz_split_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      EC_CUDA(cudaEventCreateWithFlags(&p->oz_ev_split[i], cudaEventDisableTiming));
+      EC_CUDA(cudaEventCreateWithFlags(&p->oz_ev_gemm[i], cudaEventDisableTiming));
+    }
+  }
   auto kern = ec::oz::ozaki_gemm_kernel<OZ_S>;
   static std::atomic<uint64_t> configured{0};
   const uint64_t bit = 1ull << (p->device & 63);
@@ -550,28 +566,67 @@ int ozaki_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
   // op(A)(r, q): N -> A[r + q*lda]; T -> A[r*lda + q].  op(B)^T(j, q) = op(B)(q, j): N -> B[j*ldb + q]; T -> B[q*ldb + j]
   const int64_t a_rs = transa ? lda : 1, a_ks = transa ? 1 : lda;
   const int64_t b_rs = transb ? 1 : ldb, b_ks = transb ? ldb : 1;
-  if (!a_batched && (rc = oz_split(p, A, a_rs, a_ks, 0, m, k, Kp, 1, p->oz_planes_a, p->oz_scale_a, p->oz_amax))) return rc;
-  if (!b_batched && (rc = oz_split(p, B, b_rs, b_ks, 0, n, k, Kp, 1, p->oz_planes_b, p->oz_scale_b, p->oz_amax))) return rc;
-  for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
-    const int64_t nb = std::min(chunk, batch - b0);
-    if (a_batched && (rc = oz_split(p, A + b0 * stride_a, a_rs, a_ks, stride_a, m, k, Kp, nb, p->oz_planes_a, p->oz_scale_a, p->oz_amax))) return rc;
-    if (b_batched && (rc = oz_split(p, B + b0 * stride_b, b_rs, b_ks, stride_b, n, k, Kp, nb, p->oz_planes_b, p->oz_scale_b, p->oz_amax))) return rc;
+  unsigned long long *amax_shared = p->oz_amax, *amax_buf[2] = {p->oz_amax + am_b / 8, p->oz_amax + 2 * (am_b / 8)};
+  if (!a_batched && (rc = oz_split(p, A, a_rs, a_ks, 0, m, k, Kp, 1, p->oz_planes_a, p->oz_scale_a, amax_shared))) return rc;
+  if (!b_batched && (rc = oz_split(p, B, b_rs, b_ks, 0, n, k, Kp, 1, p->oz_planes_b, p->oz_scale_b, amax_shared))) return rc;
+
+  cudaStream_t main_stream = p->stream;
+  // split of chunk c into buffer c & 1, on the side stream when pipelined
+  auto split_chunk = [&](int64_t c) -> int {
+    const int64_t b0 = c * chunk, nb = std::min(chunk, batch - b0);
+    const int buf = pipelined ? (int)(c & 1) : 0;
+    if (pipelined) {
+      p->stream = p->oz_split_stream;
+      if (c >= 2) EC_CUDA(cudaStreamWaitEvent(p->oz_split_stream, p->oz_ev_gemm[buf], 0));   // buffer consumed
+    }
+    int r = EC_OK;
+    if (a_batched)
+      r = oz_split(p, A + b0 * stride_a, a_rs, a_ks, stride_a, m, k, Kp, nb, p->oz_planes_a + buf * pa,
+                   p->oz_scale_a + buf * (sa_b / 8), amax_buf[buf]);
+    if (!r && b_batched)
+      r = oz_split(p, B + b0 * stride_b, b_rs, b_ks, stride_b, n, k, Kp, nb, p->oz_planes_b + buf * pb,
+                   p->oz_scale_b + buf * (sb_b / 8), amax_buf[buf]);
+    if (pipelined) {
+      if (!r) {
+        cudaError_t e = cudaEventRecord(p->oz_ev_split[buf], p->oz_split_stream);
+        if (e != cudaSuccess) r = fail(EC_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
+      }
+      p->stream = main_stream;
+    }
+    return r;
+  };
+  if (pipelined) {
+    // the side stream starts after whatever produced the operands on the main stream
+    EC_CUDA(cudaEventRecord(p->oz_ev_gemm[0], main_stream));
+    EC_CUDA(cudaStreamWaitEvent(p->oz_split_stream, p->oz_ev_gemm[0], 0));
+  }
+  if (a_batched || b_batched) {
+    if ((rc = split_chunk(0))) { p->stream = main_stream; return rc; }
+  }
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int64_t b0 = c * chunk, nb = std::min(chunk, batch - b0);
+    const int buf = pipelined ? (int)(c & 1) : 0;
+    if (pipelined && c + 1 < nchunks && (rc = split_chunk(c + 1))) { p->stream = main_stream; return rc; }
+    if (!pipelined && c > 0 && (a_batched || b_batched) && (rc = split_chunk(c))) return rc;
+    if (pipelined) EC_CUDA(cudaStreamWaitEvent(main_stream, p->oz_ev_split[buf], 0));
     CUtensorMap tmA, tmB;
-    if ((rc = oz_tensor_map(&tmA, p->oz_planes_a, k, Kp, m, a_batched ? nb : 1, ec::oz::OM))) return rc;
-    if ((rc = oz_tensor_map(&tmB, p->oz_planes_b, k, Kp, n, b_batched ? nb : 1, ec::oz::ON))) return rc;
+    if ((rc = oz_tensor_map(&tmA, p->oz_planes_a + (a_batched ? buf * pa : 0), k, Kp, m, a_batched ? nb : 1, ec::oz::OM))) return rc;
+    if ((rc = oz_tensor_map(&tmB, p->oz_planes_b + (b_batched ? buf * pb : 0), k, Kp, n, b_batched ? nb : 1, ec::oz::ON))) return rc;
     ec::oz::GemmOzParams gp;
     gp.M = m; gp.N = n; gp.K = k; gp.batch = nb;
     gp.alpha = alpha; gp.beta = beta;
     gp.C = C + b0 * stride_c; gp.ldc = ldc; gp.stride_c = stride_c;
-    gp.sa = p->oz_scale_a; gp.sb = p->oz_scale_b;
+    gp.sa = p->oz_scale_a + (a_batched ? buf * (sa_b / 8) : 0);
+    gp.sb = p->oz_scale_b + (b_batched ? buf * (sb_b / 8) : 0);
     gp.a_batched = a_batched; gp.b_batched = b_batched;
     gp.tiles_m = (int)((m + ec::oz::OM - 1) / ec::oz::OM);
     gp.tiles_n = (int)((n + ec::oz::ON - 1) / ec::oz::ON);
     gp.total_tiles = (int64_t)gp.tiles_m * gp.tiles_n * nb;
     const int grid = (int)std::min<int64_t>(gp.total_tiles, p->sm_count);
-    kern<<<grid, ec::oz::OTHREADS, Cfg::SMEM_BYTES, p->stream>>>(tmA, tmB, gp);
+    kern<<<grid, ec::oz::OTHREADS, Cfg::SMEM_BYTES, main_stream>>>(tmA, tmB, gp);
     EC_CUDA(cudaGetLastError());
     p->launches++;
+    if (pipelined) EC_CUDA(cudaEventRecord(p->oz_ev_gemm[buf], main_stream));
   }
   p->last_kernel = "ozaki_i8_s7";
   return EC_OK;
@@ -936,6 +991,11 @@ int ec_pipeline_destroy(ec_pipeline *p) {
   if (p->oz_scale_a) cudaFree(p->oz_scale_a);
   if (p->oz_scale_b) cudaFree(p->oz_scale_b);
   if (p->oz_amax) cudaFree(p->oz_amax);
+  if (p->oz_split_stream) cudaStreamDestroy(p->oz_split_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (p->oz_ev_split[i]) cudaEventDestroy(p->oz_ev_split[i]);
+    if (p->oz_ev_gemm[i]) cudaEventDestroy(p->oz_ev_gemm[i]);
+  }
   if (p->owns_stream) cudaStreamDestroy(p->stream);
   delete p;
   return EC_OK;

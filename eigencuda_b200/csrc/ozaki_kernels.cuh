@@ -380,8 +380,14 @@ __global__ void __launch_bounds__(OTHREADS, 1)
         uint32_t v[64];
         tmem_ld_x64(tmem + ((uint32_t)(q * 32) << 16) + d * ON, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // int32 -> double without the (slow) conversion unit: 2^52 + 2^31 + v is exactly
+        // representable with the biased value in the low mantissa word, one exact DADD removes
+        // the offset; everything stays on the FP64 pipe.
 #pragma unroll
-        for (int j = 0; j < ON; ++j) acc[j] = fma((double)(int32_t)v[j], wgt, acc[j]);
+        for (int j = 0; j < ON; ++j) {
+          const double x = __hiloint2double(0x43300000, (int)(v[j] ^ 0x80000000u)) - 4503601774854144.0;
+          acc[j] = fma(x, wgt, acc[j]);
+        }
         wgt *= (1.0 / 128.0);
       }
       tc_fence_before();
