@@ -199,6 +199,10 @@ class CudaPipeline:
         check(lib.ec_fill_uniform_block(self._h, seed, matrix_id, int(dst), rows, cols, ld_dst, row0,
                                         col0, global_ld))
 
+    def set_sm_margin(self, sms):
+        """Leave `sms` SMs free for concurrent kernels (NCCL panel broadcasts during SUMMA)."""
+        check(lib.ec_pipeline_set_sm_margin(self._h, int(sms)))
+
     def set_backend(self, backend):
         """EC_BACKEND_FP64_DMMA (native, default) or EC_BACKEND_OZAKI_I8 (int8 tensor-core emulation
         with the looser bound stated in DESIGN.md)."""

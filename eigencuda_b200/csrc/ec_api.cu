@@ -222,6 +222,7 @@ struct ec_pipeline {
   unsigned *sk_flags = nullptr;
   unsigned sk_epoch = 0;
   int stream_k = 1;   // 0 disables the stream-K schedule (EC_STREAM_K=0)
+  int sm_margin = 0;  // SMs left free for concurrent kernels (NCCL during SUMMA)
   // EC_BACKEND_OZAKI_I8 workspace: digit planes and row/column scales, grown on demand
   int8_t *oz_planes_a = nullptr, *oz_planes_b = nullptr;
   double *oz_scale_a = nullptr, *oz_scale_b = nullptr;
@@ -344,11 +345,11 @@ int launch_tma_dmma(ec_pipeline *p, const CUtensorMap &tmA, const CUtensorMap &t
   int ctas = 1;
   int rc = ctas_per_sm<Cfg, AK, BK_>(p, &ctas);
   if (rc) return rc;
-  const int64_t slots = (int64_t)p->sm_count * ctas;
+  const int64_t slots = (int64_t)(p->sm_count - p->sm_margin) * ctas;
   const int64_t kblocks = (gp.K + ec::BK - 1) / ec::BK;
   int grid = (int)std::min<int64_t>(gp.total_tiles, slots);
   gp.sk_tiles = 0;
-  gp.sk_sms = p->sm_count;
+  gp.sk_sms = p->sm_count - p->sm_margin;
   gp.sk_workspace = nullptr;
   gp.sk_flags = nullptr;
   gp.sk_epoch = 0;
@@ -446,15 +447,16 @@ TileChoice choose_tile(const ec_pipeline *p, int64_t m, int64_t n, int64_t k, in
   for (const Cand &c : cands) {
     if (force >= TILE_L && force <= TILE_XS && c.id != force) continue;
     const int64_t tiles = ((m + c.bm - 1) / c.bm) * ((n + c.bn - 1) / c.bn) * batch;
-    const int64_t slots = (int64_t)p->sm_count * c.ctas;
+    const int sms = p->sm_count - p->sm_margin;
+    const int64_t slots = (int64_t)sms * c.ctas;
     const double tile_clk = (double)c.bm * c.bn * kpad / 64.0 / c.eff + c.overhead;
-    const double dp = (double)((tiles + p->sm_count - 1) / p->sm_count) * tile_clk;
+    const double dp = (double)((tiles + sms - 1) / sms) * tile_clk;
     if (dp < best) { best = dp; pick = {c.id, false}; }
     const int64_t rem = tiles % slots;
     const int64_t sk_tiles = rem + (tiles > slots ? slots : 0);
     if (allow_sk && rem != 0 && sk_tiles * kblocks >= 4 * slots) {
       // every SM does its exact share; one partial tile written and one read per CTA
-      const double sk = force_sk ? dp * 1e-3 : (double)tiles / p->sm_count * tile_clk + c.fixup;
+      const double sk = force_sk ? dp * 1e-3 : (double)tiles / sms * tile_clk + c.fixup;
       if (sk < best) { best = sk; pick = {c.id, true}; }
     }
   }
@@ -622,7 +624,7 @@ int ozaki_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
     gp.tiles_m = (int)((m + ec::oz::OM - 1) / ec::oz::OM);
     gp.tiles_n = (int)((n + ec::oz::ON - 1) / ec::oz::ON);
     gp.total_tiles = (int64_t)gp.tiles_m * gp.tiles_n * nb;
-    const int grid = (int)std::min<int64_t>(gp.total_tiles, p->sm_count);
+    const int grid = (int)std::min<int64_t>(gp.total_tiles, p->sm_count - p->sm_margin);
     kern<<<grid, ec::oz::OTHREADS, Cfg::SMEM_BYTES, main_stream>>>(tmA, tmB, gp);
     EC_CUDA(cudaGetLastError());
     p->launches++;
@@ -1019,6 +1021,12 @@ int ec_pipeline_set_backend(ec_pipeline *p, int backend) {
   return EC_OK;
 }
 int ec_pipeline_get_backend(const ec_pipeline *p) { return p ? p->backend : -1; }
+int ec_pipeline_set_sm_margin(ec_pipeline *p, int sms) {
+  if (!p) return fail(EC_ERR_ARG, "null pipeline");
+  if (sms < 0 || sms >= p->sm_count) return fail(EC_ERR_ARG, "sm margin out of range");
+  p->sm_margin = sms;
+  return EC_OK;
+}
 int64_t ec_pipeline_launch_count(const ec_pipeline *p) { return p ? p->launches : 0; }
 const char *ec_pipeline_last_kernel(const ec_pipeline *p) { return p ? p->last_kernel : "none"; }
 

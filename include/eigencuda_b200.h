@@ -147,6 +147,10 @@ int ec_tensor_stream_run(ec_pipeline *p, int kind, const double *F, int64_t f_ro
 int ec_tensor_stream_run_device(ec_pipeline *p, int kind, const double *F_dev, int64_t f_rows,
                                 int64_t f_cols, const double *tensor_dev, double *results_dev,
                                 int64_t count, int64_t t_rows, int64_t t_cols);
+/* Leave `sms` streaming multiprocessors unused by the (persistent, register-filling) GEMM kernels
+ * so that concurrent kernels -- NCCL's, during the panel broadcasts of the 2D-partitioned DGEMM --
+ * can run underneath them instead of queueing behind them.  0 (default) = use every SM. */
+int ec_pipeline_set_sm_margin(ec_pipeline *p, int sms);
 /* Engine knobs: matrices per device chunk, ring depth, staging worker threads (0 = default). */
 int ec_pipeline_set_stream_config(ec_pipeline *p, int chunk_matrices, int ring_depth,
                                   int staging_threads);
