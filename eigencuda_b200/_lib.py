@@ -50,6 +50,7 @@ SIGNATURES = {
                                     _i64, _i64, _i64]),
     "ec_tensor_stream_run_device": (_int, [_vp, _int, _dp, _i64, _i64, _dp, _dp, _i64, _i64, _i64]),
     "ec_pipeline_set_sm_margin": (_int, [_vp, _int]),
+    "ec_pipeline_set_schedule": (_int, [_vp, _int, _int]),
     "ec_pipeline_set_stream_config": (_int, [_vp, _int, _int, _int]),
     "ec_host_alloc": (_int, [C.c_size_t, C.POINTER(_vp)]),
     "ec_host_free": (_int, [_vp]),

@@ -203,6 +203,10 @@ class CudaPipeline:
         """Leave `sms` SMs free for concurrent kernels (NCCL panel broadcasts during SUMMA)."""
         check(lib.ec_pipeline_set_sm_margin(self._h, int(sms)))
 
+    def set_schedule(self, stream_k=True, one_cta_per_tile=False):
+        """Schedule policy of the GEMM kernels (see ec_pipeline_set_schedule in the C header)."""
+        check(lib.ec_pipeline_set_schedule(self._h, int(bool(stream_k)), int(bool(one_cta_per_tile))))
+
     def set_backend(self, backend):
         """EC_BACKEND_FP64_DMMA (native, default) or EC_BACKEND_OZAKI_I8 (int8 tensor-core emulation
         with the looser bound stated in DESIGN.md)."""

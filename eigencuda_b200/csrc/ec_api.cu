@@ -223,6 +223,7 @@ struct ec_pipeline {
   unsigned sk_epoch = 0;
   int stream_k = 1;   // 0 disables the stream-K schedule (EC_STREAM_K=0)
   int sm_margin = 0;  // SMs left free for concurrent kernels (NCCL during SUMMA)
+  int one_cta_per_tile = 0;  // non-persistent launch for long tiles (shared-GPU friendly)
   // EC_BACKEND_OZAKI_I8 workspace: digit planes and row/column scales, grown on demand
   int8_t *oz_planes_a = nullptr, *oz_planes_b = nullptr;
   double *oz_scale_a = nullptr, *oz_scale_b = nullptr;
@@ -373,6 +374,8 @@ int launch_tma_dmma(ec_pipeline *p, const CUtensorMap &tmA, const CUtensorMap &t
       grid = (int)slots;
     }
   }
+  if (gp.sk_tiles == 0 && p->one_cta_per_tile && kblocks >= 64 && gp.total_tiles > slots)
+    grid = (int)std::min<int64_t>(gp.total_tiles, (int64_t)1 << 30);   // one tile per CTA
   if (gp.sk_tiles > 0) {
     // CTAs wait on one another's partials: a cooperative launch guarantees co-residency.
     void *args[3] = {(void *)&tmA, (void *)&tmB, (void *)&gp};
@@ -1021,6 +1024,12 @@ int ec_pipeline_set_backend(ec_pipeline *p, int backend) {
   return EC_OK;
 }
 int ec_pipeline_get_backend(const ec_pipeline *p) { return p ? p->backend : -1; }
+int ec_pipeline_set_schedule(ec_pipeline *p, int stream_k, int one_cta_per_tile) {
+  if (!p) return fail(EC_ERR_ARG, "null pipeline");
+  p->stream_k = stream_k ? 1 : 0;
+  p->one_cta_per_tile = one_cta_per_tile ? 1 : 0;
+  return EC_OK;
+}
 int ec_pipeline_set_sm_margin(ec_pipeline *p, int sms) {
   if (!p) return fail(EC_ERR_ARG, "null pipeline");
   if (sms < 0 || sms >= p->sm_count) return fail(EC_ERR_ARG, "sm margin out of range");

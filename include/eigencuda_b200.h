@@ -151,6 +151,13 @@ int ec_tensor_stream_run_device(ec_pipeline *p, int kind, const double *F_dev, i
  * so that concurrent kernels -- NCCL's, during the panel broadcasts of the 2D-partitioned DGEMM --
  * can run underneath them instead of queueing behind them.  0 (default) = use every SM. */
 int ec_pipeline_set_sm_margin(ec_pipeline *p, int sms);
+/* Schedule policy of the GEMM kernels.  stream_k: 1 (default) lets the cost model cut the last
+ * wave along k (cooperative launch); 0 never does.  one_cta_per_tile: 1 launches one CTA per
+ * output tile instead of a persistent grid when tiles are long (K >= 1024), so that the hardware
+ * scheduler balances the work around other kernels sharing the GPU -- NCCL's during the panel
+ * broadcasts of the 2D-partitioned DGEMM, where a statically partitioned persistent grid stalls
+ * on the SMs NCCL holds.  0 (default) = persistent. */
+int ec_pipeline_set_schedule(ec_pipeline *p, int stream_k, int one_cta_per_tile);
 /* Engine knobs: matrices per device chunk, ring depth, staging worker threads (0 = default). */
 int ec_pipeline_set_stream_config(ec_pipeline *p, int chunk_matrices, int ring_depth,
                                   int staging_threads);

@@ -281,6 +281,23 @@ def test_stream_k_batched(pipe, monkeypatch):
         assert orc.rel_frobenius(got[:, :, i], orc.cpu_product(orc.fill_uniform(orc.SEED, i + 1, (n, n)), F)) <= TOL
 
 
+def test_one_cta_per_tile_schedule(pipe):
+    """The non-persistent launch (one CTA per tile, for long-K tiles on a shared GPU) computes the
+    same bits as the persistent grid."""
+    A, B = rnd(1, (1300, 1100)), rnd(2, (1100, 1800))
+    dA, dB = ec.CudaMatrix(A, pipe.get_stream()), ec.CudaMatrix(B, pipe.get_stream())
+    dC = ec.CudaMatrix(1300, 1800, pipe.get_stream())
+    pipe.set_schedule(stream_k=False, one_cta_per_tile=False)
+    pipe.gemm(dA, dB, dC)
+    want = dC.to_eigen()
+    pipe.set_schedule(stream_k=False, one_cta_per_tile=True)
+    pipe.gemm(dA, dB, dC)
+    got = dC.to_eigen()
+    pipe.set_schedule(stream_k=True, one_cta_per_tile=False)
+    assert np.array_equal(got, want)
+    assert orc.rel_frobenius(got, orc.cpu_product(A, B)) <= TOL
+
+
 def test_beta_zero_ignores_nan_in_c(pipe):
     A, B = rnd(1, (160, 96)), rnd(2, (96, 144))
     dA, dB = ec.CudaMatrix(A, pipe.get_stream()), ec.CudaMatrix(B, pipe.get_stream())

@@ -28,7 +28,8 @@ ap.add_argument("--size", type=int, default=16384, dest="n")
 ap.add_argument("--panel", type=int, default=2048, dest="kb")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--samples", type=int, default=6)
-ap.add_argument("--margin", type=int, default=-1, help="SMs left free for NCCL (-1: 8 when world > 1 else 0)")
+ap.add_argument("--margin", type=int, default=0, help="SMs left free for NCCL")
+ap.add_argument("--persistent", type=int, default=0, help="1: persistent grid + stream-K (the single-GPU default); 0: one CTA per tile, which coexists with NCCL kernels")
 args = ap.parse_args()
 
 rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -41,8 +42,10 @@ L = summa.Layout(n, n, n, world, rank)
 rg, cg = summa.make_groups(L) if world > 1 else (None, None)
 stream = torch.cuda.current_stream()
 pipe = ec.CudaPipeline(local, stream=stream.cuda_stream)
-margin = args.margin if args.margin >= 0 else (8 if world > 1 else 0)
+margin = args.margin
 pipe.set_sm_margin(margin)
+if not args.persistent:
+    pipe.set_schedule(stream_k=False, one_cta_per_tile=True)
 
 (am, ak), (bk, bn), (cm, cn) = L.a_shape, L.b_shape, L.c_shape
 A_loc = torch.empty((ak, am), dtype=torch.float64, device=dev)     # column-major am x ak
@@ -99,7 +102,7 @@ if rank == 0:
                       "n_gpus": world, "ms": ms, "tflops": tf, "tflops_per_gpu": tf / world,
                       "frac_of_fp64_peak": tf / world / 37.22496,
                       "sampled_rel_err_vs_long_double": float(w.item()),
-                      "sm_margin": margin, "panel_bytes_received_per_gpu": (am * (n - ak) + (n - bk) * bn) * 8}), flush=True)
+                      "sm_margin": margin, "persistent": bool(args.persistent), "panel_bytes_received_per_gpu": (am * (n - ak) + (n - bk) * bn) * 8}), flush=True)
 pipe.close()
 if world > 1:
     dist.destroy_process_group()
