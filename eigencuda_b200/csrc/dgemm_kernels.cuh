@@ -64,7 +64,7 @@ struct TileCfg {
   static_assert(!REGSPLIT || CONSUMER_WARPS % 4 == 0, "setmaxnreg works on whole warpgroups");
 };
 //                    BM   BN   WM  WN  ST CTAs regsplit
-using CfgL  = TileCfg<128, 128, 64, 32, 5, 1, true>;    // 8 consumer warps, 160 KiB, 232 regs
+using CfgL  = TileCfg<128, 128, 64, 32, 5, 1, true>;    // 8 consumer warps, 160 KiB, 232 regs (6 stages measured: no gain)
 using CfgS  = TileCfg< 64,  64, 32, 32, 4, 2, false>;   // 4 consumer warps,  64 KiB, 2 CTAs/SM
 using CfgXS = TileCfg< 64,  32, 32, 16, 4, 3, false>;   // 4 consumer warps,  48 KiB, 3 CTAs/SM
 // (A 128x64 / 2 CTAs-per-SM variant and register-split variants of the small tiles were measured

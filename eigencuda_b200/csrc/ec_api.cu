@@ -224,6 +224,14 @@ struct ec_pipeline {
   int stream_k = 1;   // 0 disables the stream-K schedule (EC_STREAM_K=0)
   int sm_margin = 0;  // SMs left free for concurrent kernels (NCCL during SUMMA)
   int one_cta_per_tile = 0;  // non-persistent launch for long tiles (shared-GPU friendly)
+  // small direct-mapped cache of encoded tensor maps: the compat loop and every tensor-stream
+  // chunk reuse the same few device buffers, and cuTensorMapEncodeTiled costs about a microsecond
+  struct TmapEntry {
+    const void *ptr = nullptr;
+    int64_t inner = 0, outer = 0, batch = 0, ld = 0, stride = 0;
+    int box_outer = 0;
+    CUtensorMap map;
+  } tmap_cache[16];
   // EC_BACKEND_OZAKI_I8 workspace: digit planes and row/column scales, grown on demand
   int8_t *oz_planes_a = nullptr, *oz_planes_b = nullptr;
   double *oz_scale_a = nullptr, *oz_scale_b = nullptr;
@@ -286,27 +294,40 @@ bool tma_ok(const Operand &o, int64_t batch) {
   return true;
 }
 
-int make_tensor_map(CUtensorMap *tm, const Operand &o, int64_t batch, int tile_extent) {
+int make_tensor_map(ec_pipeline *p, CUtensorMap *tm, const Operand &o, int64_t batch, int tile_extent) {
+  const bool batched = batch > 1 && o.stride != 0;
+  const int64_t inner = o.kmajor ? o.k : o.mn, outer = o.kmajor ? o.mn : o.k;
+  const int box_outer = o.kmajor ? tile_extent : ec::BK;
+  const int64_t nb = batched ? batch : 1, st = batched ? o.stride : 0;
+  // cache lookup
+  uint64_t hsh = (uint64_t)(uintptr_t)o.ptr * 0x9E3779B97F4A7C15ull ^ (uint64_t)inner * 0xBF58476D1CE4E5B9ull ^
+                 (uint64_t)outer * 0x94D049BB133111EBull ^ (uint64_t)o.ld * 31 ^ (uint64_t)box_outer;
+  ec_pipeline::TmapEntry &e = p->tmap_cache[(hsh >> 40) & 15];
+  if (e.ptr == o.ptr && e.inner == inner && e.outer == outer && e.batch == nb && e.ld == o.ld && e.stride == st &&
+      e.box_outer == box_outer) {
+    *tm = e.map;
+    return EC_OK;
+  }
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) return fail(EC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  const bool batched = batch > 1 && o.stride != 0;
   cuuint64_t dims[3], strides[2];
   cuuint32_t box[3], estr[3] = {1, 1, 1};
-  const int64_t inner = o.kmajor ? o.k : o.mn, outer = o.kmajor ? o.mn : o.k;
   dims[0] = (cuuint64_t)inner;
   dims[1] = (cuuint64_t)outer;
-  dims[2] = (cuuint64_t)(batched ? batch : 1);
+  dims[2] = (cuuint64_t)nb;
   strides[0] = (cuuint64_t)o.ld * 8;
   // stride of the (possibly degenerate) batch dimension: any legal multiple of 16 when unused
   strides[1] = batched ? (cuuint64_t)o.stride * 8 : (cuuint64_t)o.ld * 8 * (cuuint64_t)std::max<int64_t>(outer, 1);
   box[0] = 16;
-  box[1] = o.kmajor ? (cuuint32_t)tile_extent : (cuuint32_t)ec::BK;
+  box[1] = (cuuint32_t)box_outer;
   box[2] = 1;
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)o.ptr, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(EC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  e.ptr = o.ptr; e.inner = inner; e.outer = outer; e.batch = nb; e.ld = o.ld; e.stride = st; e.box_outer = box_outer;
+  e.map = *tm;
   return EC_OK;
 }
 
@@ -395,9 +416,9 @@ int run_tma_dmma(ec_pipeline *p, const Operand &oa, const Operand &ob, int64_t m
                  int64_t stride_a, int64_t stride_b, int64_t batch, bool want_sk,
                  const char *const names[8]) {
   CUtensorMap tmA, tmB;
-  int rc = make_tensor_map(&tmA, oa, batch, Cfg::BM);
+  int rc = make_tensor_map(p, &tmA, oa, batch, Cfg::BM);
   if (rc) return rc;
-  rc = make_tensor_map(&tmB, ob, batch, Cfg::BN);
+  rc = make_tensor_map(p, &tmB, ob, batch, Cfg::BN);
   if (rc) return rc;
   ec::GemmParams gp;
   gp.M = m; gp.N = n; gp.K = k; gp.batch = batch;

@@ -23,7 +23,7 @@
 //   ozaki_gemm_kernel<S>    persistent, warp-specialised: warp 0 = TMA producer (4D tensor maps,
 //                           one box per operand per stage covering all S planes, 64B swizzle),
 //                           warp 1 = MMA issuer (S(S+1)/2 * 2 tcgen05.mma per 64-byte k-chunk into
-//                           S accumulators of 128x64 s32 = 448 TMEM columns), warps 2-5 = epilogue
+//                           S accumulators of 128x64 s32 = 448 TMEM columns), warps 2-9 = epilogue
 //                           (tcgen05.ld, exact power-of-two weighting in FP64, coalesced stores).
 #pragma once
 #include <cuda.h>
@@ -39,7 +39,7 @@ constexpr int OM = 128;     // CTA tile rows (UMMA M)
 constexpr int ON = 64;      // CTA tile columns (UMMA N); S accumulators x 64 columns <= 512
 constexpr int OBK = 64;     // bytes of K per stage = two K=32 MMAs; 64-byte swizzle rows
 constexpr int OSTAGES = 2;
-constexpr int OTHREADS = 192;
+constexpr int OTHREADS = 320;   // producer warp, MMA warp, 8 epilogue warps
 
 // ---------------------------------------------------------------------------------------------
 // splitting
@@ -234,6 +234,19 @@ __device__ __forceinline__ void tmem_ld_x64(uint32_t taddr, uint32_t (&r)[64]) {
       : "memory");
 }
 
+// 32 consecutive 32-bit TMEM columns of this warp's 32 lanes.
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+        "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 template <int S>
 struct OzCfg {
   static constexpr int A_BYTES = S * OM * OBK, B_BYTES = S * ON * OBK;
@@ -264,7 +277,7 @@ __global__ void __launch_bounds__(OTHREADS, 1)
       mbar_init(empty_bar(s), 1);   // one tcgen05.commit per stage
     }
     mbar_init(tmem_full, 1);        // one tcgen05.commit per tile
-    mbar_init(tmem_empty, 4);       // one arrive per epilogue warp
+    mbar_init(tmem_empty, 8);       // one arrive per epilogue warp
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -351,10 +364,14 @@ __global__ void __launch_bounds__(OTHREADS, 1)
       }
     }
   } else {
-    // ===================== epilogue warps (2..5): TMEM -> FP64 -> global =====================
+    // ===================== epilogue warps (2..9): TMEM -> FP64 -> global =====================
+    // Two warps per TMEM lane quarter, each taking 32 of the tile's 64 columns, so that one
+    // warp's TMEM-load latency overlaps the other's FP64 work on the same SM sub-partition.
+    constexpr int EN = ON / 2;
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;          // which 32 columns
     const int row_in_tile = q * 32 + lane;
-    const int et = threadIdx.x - 64;           // 0..127
+    const int et = threadIdx.x - 64;           // 0..255
     uint32_t tphase = 0;
     for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = (int)(tile / tiles_per_problem);
@@ -363,28 +380,28 @@ __global__ void __launch_bounds__(OTHREADS, 1)
       oz_tile_coords(r, p.tiles_m, p.tiles_n, tm, tn);
       const int m0 = tm * OM, n0 = tn * ON;
       // column scales of this tile (visible to all epilogue warps after the named barrier)
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's readers are done
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // previous tile's readers are done
       if (et < ON) {
         const int64_t col = n0 + et;
         colscale[et] = col < p.N ? p.sb[(p.b_batched ? (int64_t)b * p.N : 0) + col] : 0.0;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(tmem_full, tphase);
       tc_fence_after();
-      double acc[ON];
+      double acc[EN];
 #pragma unroll
-      for (int j = 0; j < ON; ++j) acc[j] = 0.0;
+      for (int j = 0; j < EN; ++j) acc[j] = 0.0;
       double wgt = 1.0 / 16384.0;              // 128^-(d+2)
 #pragma unroll 1
       for (int d = 0; d < S; ++d) {
-        uint32_t v[64];
-        tmem_ld_x64(tmem + ((uint32_t)(q * 32) << 16) + d * ON, v);
+        uint32_t v[EN];
+        tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + d * ON + half * EN, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         // int32 -> double without the (slow) conversion unit: 2^52 + 2^31 + v is exactly
         // representable with the biased value in the low mantissa word, one exact DADD removes
         // the offset; everything stays on the FP64 pipe.
 #pragma unroll
-        for (int j = 0; j < ON; ++j) {
+        for (int j = 0; j < EN; ++j) {
           const double x = __hiloint2double(0x43300000, (int)(v[j] ^ 0x80000000u)) - 4503601774854144.0;
           acc[j] = fma(x, wgt, acc[j]);
         }
@@ -400,10 +417,10 @@ __global__ void __launch_bounds__(OTHREADS, 1)
         double *Crow = p.C + (int64_t)b * p.stride_c + row;
         const bool use_beta = p.beta != 0.0;
 #pragma unroll
-        for (int j = 0; j < ON; ++j) {
-          const int64_t col = n0 + j;
+        for (int j = 0; j < EN; ++j) {
+          const int64_t col = n0 + half * EN + j;
           if (col < p.N) {
-            double v = rs * colscale[j] * acc[j];
+            double v = rs * colscale[half * EN + j] * acc[j];
             if (use_beta) v += p.beta * Crow[col * p.ldc];
             Crow[col * p.ldc] = v;
           }
