@@ -436,6 +436,61 @@ def test_tensor_stream_kinds(pipe, kind, pinned):
         b.close()
 
 
+def test_tensor_stream_mixed_host_memory_and_device_fixed(pipe):
+    """Pinned inputs with pageable outputs (and the reverse), and a fixed operand that already
+    lives on the device (what the multi-GPU broadcast leaves behind): detected per buffer."""
+    import ctypes as C
+    n, count = 128, 11
+    F = orc.fill_uniform(orc.SEED, 0, (n, n))
+    dF = ec.CudaMatrix(F, pipe.get_stream())
+    pin = ec.PinnedBuffer((n, n, count))
+    for i in range(count):
+        pin.array[:, :, i] = orc.fill_uniform(orc.SEED, i + 1, (n, n))
+    pinned_ts = [pin.array[:, :, i] for i in range(count)]
+    pageable_ts = [np.asfortranarray(t.copy()) for t in pinned_ts]
+    want = orc.tensor_stream("right", F, pageable_ts, flavour="fast")
+    pipe.set_stream_config(3, 3, 2)
+    pout = ec.PinnedBuffer((n, n, count))
+    for ts, outs in ((pinned_ts, None), (pageable_ts, [pout.array[:, :, i] for i in range(count)])):
+        res = pipe.tensor_stream(ec.EC_STREAM_RIGHT, F, ts, results=outs)
+        for r, w in zip(res, want):
+            assert orc.rel_frobenius(r, w) <= TOL
+    # fixed operand passed as a DEVICE pointer
+    outs = [np.empty((n, n), order="F") for _ in range(count)]
+    ip = (C.c_void_p * count)(*[t.ctypes.data for t in pageable_ts])
+    op = (C.c_void_p * count)(*[o.ctypes.data for o in outs])
+    pipe.tensor_stream_raw(ec.EC_STREAM_RIGHT, dF.data(), n, n, ip, op, count, n, n)
+    for r, w in zip(outs, want):
+        assert orc.rel_frobenius(r, w) <= TOL
+    pipe.set_stream_config(0, 0, 0)
+    pin.close()
+    pout.close()
+
+
+def test_operands_created_on_another_stream_and_two_pipelines(pipe):
+    """gemm on pipeline A with matrices created on pipeline B's stream (the reference is ordered by
+    the legacy NULL stream there; here the dependency is explicit), and two pipelines used in
+    alternation, each with its own stream-K workspace."""
+    other = ec.CudaPipeline(0)
+    try:
+        A, B = rnd(11, (1280, 520)), rnd(12, (520, 1280))
+        dA = ec.CudaMatrix(A, other.get_stream())
+        dB = ec.CudaMatrix(B, other.get_stream())
+        dC = ec.CudaMatrix(1280, 1280, other.get_stream())
+        pipe.gemm(dA, dB, dC)                       # runs on pipe's stream, operands from `other`
+        got = dC.to_eigen()                         # downloads on `other`'s stream
+        want = orc.cpu_product(A, B)
+        assert orc.rel_frobenius(got, want) <= TOL
+        dC2 = ec.CudaMatrix(1280, 1280, pipe.get_stream())
+        for _ in range(4):
+            pipe.gemm(dA, dB, dC2)
+            other.gemm(dA, dB, dC)
+        assert np.array_equal(dC2.to_eigen(), dC.to_eigen())
+        assert orc.rel_frobenius(dC.to_eigen(), want) <= TOL
+    finally:
+        other.close()
+
+
 def test_tensor_stream_rectangular_reference_order(pipe, ref):
     """T_i (r x c) * F (c x c2): the reference's gemm(cuma_B, cuma_A, cuma_C) order, vs the
     unmodified reference run on the same inputs."""
