@@ -458,12 +458,15 @@ TileChoice choose_tile(const ec_pipeline *p, int64_t m, int64_t n, int64_t k, in
     allow_sk = atoi(e) != 0;
     force_sk = atoi(e) == 2;
   }
-  // eff: fraction of the DMMA issue rate the main loop sustains; overhead: exposed clocks per
-  // tile; fixup: exposed clocks of one stream-K tail (publish partial, wait, read, epilogue)
-  struct Cand { int id, bm, bn, ctas; double eff, overhead, fixup; };
-  const Cand cands[3] = {{TILE_L, 128, 128, 1, 0.987, 2300.0, 30000.0},
-                         {TILE_S, 64, 64, 2, 0.955, 1200.0, 12000.0},
-                         {TILE_XS, 64, 32, 3, 0.90, 800.0, 8000.0}};
+  // eff[r-1]: fraction of the DMMA issue rate the main loop sustains with r CTAs resident per SM
+  // (the 4-warp tiles put one warp on each SM sub-partition per CTA and hide their LDS latency
+  // badly until a second or third CTA shares the SM); overhead: exposed clocks per tile; fixup:
+  // exposed clocks of one stream-K tail (publish partial, wait, read, epilogue).  Fitted to
+  // profiles/r01_tile_sweep*.json and profiles/r01_small_probe.txt (back-to-back launches).
+  struct Cand { int id, bm, bn, ctas; double eff[3], overhead, fixup; };
+  const Cand cands[3] = {{TILE_L, 128, 128, 1, {0.987, 0.987, 0.987}, 2300.0, 30000.0},
+                         {TILE_S, 64, 64, 2, {0.59, 0.955, 0.955}, 1200.0, 17000.0},
+                         {TILE_XS, 64, 32, 3, {0.50, 0.76, 0.80}, 800.0, 20000.0}};
   const double kpad = (double)((k + 15) / 16 * 16);
   const int64_t kblocks = (k + 15) / 16;
   double best = 1e300;
@@ -473,14 +476,17 @@ TileChoice choose_tile(const ec_pipeline *p, int64_t m, int64_t n, int64_t k, in
     const int64_t tiles = ((m + c.bm - 1) / c.bm) * ((n + c.bn - 1) / c.bn) * batch;
     const int sms = p->sm_count - p->sm_margin;
     const int64_t slots = (int64_t)sms * c.ctas;
-    const double tile_clk = (double)c.bm * c.bn * kpad / 64.0 / c.eff + c.overhead;
+    const int64_t resident = std::max<int64_t>(1, std::min<int64_t>(c.ctas, (tiles + sms - 1) / sms));
+    const double tile_clk = (double)c.bm * c.bn * kpad / 64.0 / c.eff[resident - 1] + c.overhead;
     const double dp = (double)((tiles + sms - 1) / sms) * tile_clk;
     if (dp < best) { best = dp; pick = {c.id, false}; }
     const int64_t rem = tiles % slots;
     const int64_t sk_tiles = rem + (tiles > slots ? slots : 0);
     if (allow_sk && rem != 0 && sk_tiles * kblocks >= 4 * slots) {
       // every SM does its exact share; one partial tile written and one read per CTA
-      const double sk = force_sk ? dp * 1e-3 : (double)tiles / sms * tile_clk + c.fixup;
+      // the stream-K grid fills every slot, so the SM runs at its full-occupancy efficiency
+      const double tile_clk_sk = (double)c.bm * c.bn * kpad / 64.0 / c.eff[c.ctas - 1] + c.overhead;
+      const double sk = force_sk ? dp * 1e-3 : (double)tiles / sms * tile_clk_sk + c.fixup;
       if (sk < best) { best = sk; pick = {c.id, true}; }
     }
   }
