@@ -664,3 +664,64 @@ def test_ozaki_tensor_stream_and_batch_chunking(ozaki, monkeypatch):
         for r, w in zip(res, orc.tensor_stream(name, F, ts, flavour="fast")):
             assert orc.rel_frobenius(r, w) <= OZ_TOL
     assert ozaki.last_kernel() == "ozaki_i8_s7"
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded fuzz over shapes / layouts / paddings / scalars / batching, both backends
+# ---------------------------------------------------------------------------------------------
+def _fuzz_case(rng):
+    big = rng.random() < 0.3
+    hi = 900 if big else 260
+    m, n, k = (int(rng.integers(1, hi)) for _ in range(3))
+    if rng.random() < 0.5:                       # make TMA-addressable shapes common
+        m, n, k = m + m % 2, n + n % 2, k + k % 2
+    ta, tb = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+    pads = [int(rng.choice([0, 0, 2, 3, 8])) for _ in range(3)]
+    alpha = float(rng.choice([1.0, -0.5, 2.25]))
+    beta = float(rng.choice([0.0, 0.0, 1.0, -1.5]))
+    return m, n, k, ta, tb, pads, alpha, beta
+
+
+@pytest.mark.parametrize("backend", ["native", "ozaki"])
+def test_fuzz_dgemm(pipe, backend):
+    rng = np.random.default_rng(20200210 if backend == "native" else 20200211)
+    pipe.set_backend(ec.EC_BACKEND_OZAKI_I8 if backend == "ozaki" else ec.EC_BACKEND_FP64_DMMA)
+    kernels = set()
+    try:
+        for case in range(70):
+            m, n, k, ta, tb, pads, alpha, beta = _fuzz_case(rng)
+            got, want = run_dgemm(pipe, ta, tb, m, n, k, alpha, beta, *pads, seed=1000 + case)
+            kernels.add(pipe.last_kernel())
+            err = orc.rel_frobenius(got, want)
+            assert err <= TOL, (case, m, n, k, ta, tb, pads, alpha, beta, pipe.last_kernel(), err)
+    finally:
+        pipe.set_backend(ec.EC_BACKEND_FP64_DMMA)
+    assert "simt" in kernels and any(x.startswith("tma_dmma") for x in kernels)
+    if backend == "ozaki":
+        assert "ozaki_i8_s7" in kernels
+
+
+def test_fuzz_batched(pipe):
+    rng = np.random.default_rng(7)
+    for case in range(12):
+        m, n, k = (int(2 * rng.integers(8, 200)) for _ in range(3))
+        batch = int(rng.integers(1, 40))
+        ta, tb = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        shared_b = bool(rng.integers(0, 2))
+        a_shape = (k, m) if ta else (m, k)
+        b_shape = (n, k) if tb else (k, n)
+        As = np.asfortranarray(rng.uniform(-1, 1, a_shape + (batch,)))
+        Bs = np.asfortranarray(rng.uniform(-1, 1, b_shape + ((1,) if shared_b else (batch,))))
+        dA = ec.CudaMatrix(As.reshape(a_shape[0], -1, order="F"), pipe.get_stream())
+        dB = ec.CudaMatrix(Bs.reshape(b_shape[0], -1, order="F"), pipe.get_stream())
+        dC = ec.CudaMatrix(m, n * batch, pipe.get_stream())
+        for backend in (ec.EC_BACKEND_FP64_DMMA, ec.EC_BACKEND_OZAKI_I8):
+            pipe.set_backend(backend)
+            pipe.dgemm_strided_batched(int(ta), int(tb), m, n, k, 1.0, dA.data(), a_shape[0], a_shape[0] * a_shape[1],
+                                       dB.data(), b_shape[0], 0 if shared_b else b_shape[0] * b_shape[1], 0.0,
+                                       dC.data(), m, m * n, batch)
+            got = dC.to_eigen().reshape(m, n, batch, order="F")
+            for i in range(batch):
+                want = orc.dgemm(As[:, :, i], Bs[:, :, 0 if shared_b else i], ta, tb, flavour="fast")
+                assert orc.rel_frobenius(got[:, :, i], want) <= TOL, (case, m, n, k, batch, ta, tb, shared_b, pipe.last_kernel())
+        pipe.set_backend(ec.EC_BACKEND_FP64_DMMA)
