@@ -312,7 +312,8 @@ def main():
     # ---- e2e: through the C-ABI tensor-stream call with pinned host buffers ----
     e2e = None
     if not args.no_e2e:
-        ecount = args.e2e_count or count
+        # per-rank pinned buffers: 2 x 8 GiB at the default size; halve from 4 ranks up (host RAM)
+        ecount = args.e2e_count or (count if world <= 2 else max(64, count // 2))
         pin_in = pin_out = None
         while ecount >= 64:
             try:
@@ -523,6 +524,12 @@ def main():
                 traffic = json.load(open(tpath))["bytes_per_matrix"] * count
             except Exception:
                 traffic = None
+        hbm_frac = None
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            hbm_frac = (count * 2 * elems * 8 + elems * 8) / (kernel_ms * 1e-3) / 1e9 / mp["hbm_gbs"]
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "achieved": achieved_tflops, "peak": FP64_DATASHEET_TFLOPS,
                     "unit": "TFLOP/s", "frac": achieved_tflops / FP64_DATASHEET_TFLOPS, "traffic": traffic,
                     "kernel": "dgemm_tma_dmma_kernel<CfgL,NN> (FP64 DMMA, mma.sync.m8n8k4), variant " + kernel_name,
@@ -530,6 +537,7 @@ def main():
                     "algorithmic_flops_per_launch": count * flops_per_matrix,
                     "algorithmic_hbm_bytes_per_launch": count * 2 * elems * 8 + elems * 8,
                     "hbm_gbs_achieved": (count * 2 * elems * 8 + elems * 8) / (kernel_ms * 1e-3) / 1e9,
+                    "hbm_frac_of_measured_peak": hbm_frac,
                     "peak_source": "datasheet-derived FP64 peak 148 SM x 128 flop/clk x 1.965 GHz "
                                    "(MEASURED_PEAKS.json has no FP64 figure; of fallback/datasheet)"}
         if peaks:
