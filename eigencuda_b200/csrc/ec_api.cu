@@ -486,7 +486,11 @@ TileChoice choose_tile(const ec_pipeline *p, int64_t m, int64_t n, int64_t k, in
       // every SM does its exact share; one partial tile written and one read per CTA
       // the stream-K grid fills every slot, so the SM runs at its full-occupancy efficiency
       const double tile_clk_sk = (double)c.bm * c.bn * kpad / 64.0 / c.eff[c.ctas - 1] + c.overhead;
-      const double sk = force_sk ? dp * 1e-3 : (double)tiles / sms * tile_clk_sk + c.fixup;
+      // with far fewer tiles than CTAs a tile is cut into several partials and its owner adds
+      // them one after the other: the exposed tail grows with the partials per tile
+      const double splits = std::max(1.0, (double)slots / (double)tiles);
+      const double sk = force_sk ? dp * 1e-3
+                                 : (double)tiles / sms * tile_clk_sk + c.fixup * (1.0 + 0.35 * (splits - 1.0));
       if (sk < best) { best = sk; pick = {c.id, true}; }
     }
   }
