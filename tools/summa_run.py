@@ -29,6 +29,7 @@ ap.add_argument("--panel", type=int, default=2048, dest="kb")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--samples", type=int, default=6)
 ap.add_argument("--margin", type=int, default=0, help="SMs left free for NCCL")
+ap.add_argument("--backend", default="native", choices=["native", "ozaki"], help="arithmetic of the local panel products")
 ap.add_argument("--persistent", type=int, default=0, help="1: persistent grid + stream-K (the single-GPU default); 0: one CTA per tile, which coexists with NCCL kernels")
 args = ap.parse_args()
 
@@ -46,6 +47,8 @@ margin = args.margin
 pipe.set_sm_margin(margin)
 if not args.persistent:
     pipe.set_schedule(stream_k=False, one_cta_per_tile=True)
+if args.backend == "ozaki":
+    pipe.set_backend(ec.EC_BACKEND_OZAKI_I8)
 
 (am, ak), (bk, bn), (cm, cn) = L.a_shape, L.b_shape, L.c_shape
 A_loc = torch.empty((ak, am), dtype=torch.float64, device=dev)     # column-major am x ak
@@ -99,10 +102,10 @@ if rank == 0:
     tf = 2.0 * n ** 3 / (ms * 1e-3) / 1e12
     print(json.dumps({"workload": f"single DGEMM n={n}, 2D block partition {L.P}x{L.Q}, SUMMA panels kb={args.kb}, "
                                   "NCCL broadcasts double-buffered against the DMMA kernel",
-                      "n_gpus": world, "ms": ms, "tflops": tf, "tflops_per_gpu": tf / world,
+                      "n_gpus": world, "ms": ms, "tflops": tf, "tflops_per_gpu": tf / world, "local_kernel": pipe.last_kernel(),
                       "frac_of_fp64_peak": tf / world / 37.22496,
                       "sampled_rel_err_vs_long_double": float(w.item()),
-                      "sm_margin": margin, "persistent": bool(args.persistent), "panel_bytes_received_per_gpu": (am * (n - ak) + (n - bk) * bn) * 8}), flush=True)
+                      "backend": args.backend, "sm_margin": margin, "persistent": bool(args.persistent), "panel_bytes_received_per_gpu": (am * (n - ak) + (n - bk) * bn) * 8}), flush=True)
 pipe.close()
 if world > 1:
     dist.destroy_process_group()
