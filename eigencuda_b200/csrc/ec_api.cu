@@ -505,8 +505,9 @@ constexpr int OZ_S = 7;   // digit planes: 49 fractional bits below each row/col
 
 // Shapes the emulation takes; everything else runs the native FP64 kernels (which are at least
 // as accurate).  K <= 65536 keeps the int32 accumulators exact for 7 planes.
+constexpr int64_t OZ_MAX_K = 65536;   // 7 * 65536 * 65^2 < 2^31: deeper products are cut along k
 bool ozaki_eligible(int64_t m, int64_t n, int64_t k) {
-  return k >= 64 && k <= 65536 && m >= 64 && n >= 32 && m * n * k >= (int64_t)128 * 128 * 128 &&
+  return k >= 64 && m >= 64 && n >= 32 && m * n * k >= (int64_t)128 * 128 * 128 &&
          m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31);
 }
 
@@ -695,9 +696,16 @@ int dgemm_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
   }
 
   if (p->backend == EC_BACKEND_OZAKI_I8 && ozaki_eligible(m, n, k)) {
-    const int rc = ozaki_dispatch(p, transa, transb, m, n, k, alpha, A, lda, stride_a, B, ldb, stride_b, beta,
-                                  C, ldc, stride_c, batch);
-    return rc;
+    // k beyond what the int32 accumulators hold exactly: consecutive k-chunks, accumulated with beta = 1
+    for (int64_t k0 = 0; k0 < k; k0 += OZ_MAX_K) {
+      const int64_t kc = std::min(OZ_MAX_K, k - k0);
+      const double *Ak = A + (transa ? k0 : k0 * lda);
+      const double *Bk = B + (transb ? k0 * ldb : k0);
+      const int rc = ozaki_dispatch(p, transa, transb, m, n, kc, alpha, Ak, lda, stride_a, Bk, ldb, stride_b,
+                                    k0 == 0 ? beta : 1.0, C, ldc, stride_c, batch);
+      if (rc) return rc;
+    }
+    return EC_OK;
   }
 
   Operand oa{A, lda, stride_a, transa == EC_OP_T, m, k};

@@ -637,6 +637,20 @@ def test_ozaki_stated_bound_on_badly_scaled_rows(ozaki):
     assert np.array_equal(dC.to_eigen(), got * 2.0 ** 40)
 
 
+def test_ozaki_deep_k_is_chunked(ozaki):
+    """K beyond 65536 (where 7 planes would overflow the exact int32 accumulators) is cut along k
+    and accumulated with beta = 1; a last chunk shorter than 64 still goes through."""
+    m, n, k = 128, 64, 65536 + 4096 + 24
+    A, B = rnd(3, (m, k)), rnd(4, (k, n))
+    Cin = rnd(5, (m, n))
+    dA, dB = ec.CudaMatrix(A, ozaki.get_stream()), ec.CudaMatrix(B, ozaki.get_stream())
+    dC = ec.CudaMatrix(Cin, ozaki.get_stream())
+    ozaki.dgemm(0, 0, m, n, k, 0.5, dA.data(), m, dB.data(), k, -2.0, dC.data(), m)
+    assert ozaki.last_kernel() == "ozaki_i8_s7"
+    want = orc.dgemm(A, B, alpha=0.5, beta=-2.0, Cin=Cin, flavour="ld")
+    assert orc.rel_frobenius(dC.to_eigen(), want) <= OZ_TOL
+
+
 def test_ozaki_nan_and_zero_rows(ozaki):
     m, n, k = 256, 128, 256
     A, B = rnd(1, (m, k)), rnd(2, (k, n))
