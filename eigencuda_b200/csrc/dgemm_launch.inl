@@ -1,0 +1,231 @@
+// eigencuda_b200/csrc/dgemm_launch.inl -- native FP64 path: tensor maps, stream-K workspace, kernel launch, tile / schedule cost model
+// Part of the single translation unit ec_api.cu (included there, in order); not a standalone header.
+#pragma once
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------
+struct Operand {
+  const double *ptr;
+  int64_t ld, stride;
+  bool kmajor;     // contiguous along k
+  int64_t mn, k;   // extents of op(X): mn x k
+};
+
+bool tma_ok(const Operand &o, int64_t batch) {
+  if (((uintptr_t)o.ptr & 15u) != 0) return false;
+  if ((o.ld & 1) != 0) return false;                       // row pitch must be a multiple of 16 B
+  if (batch > 1 && o.stride != 0 && (o.stride & 1) != 0) return false;
+  if (o.mn >= ((int64_t)1 << 31) || o.k >= ((int64_t)1 << 31)) return false;
+  if (o.ld * 8 >= ((int64_t)1 << 40) || o.stride * 8 >= ((int64_t)1 << 40)) return false;
+  return true;
+}
+
+int make_tensor_map(ec_pipeline *p, CUtensorMap *tm, const Operand &o, int64_t batch, int tile_extent) {
+  const bool batched = batch > 1 && o.stride != 0;
+  const int64_t inner = o.kmajor ? o.k : o.mn, outer = o.kmajor ? o.mn : o.k;
+  const int box_outer = o.kmajor ? tile_extent : ec::BK;
+  const int64_t nb = batched ? batch : 1, st = batched ? o.stride : 0;
+  // cache lookup
+  uint64_t hsh = (uint64_t)(uintptr_t)o.ptr * 0x9E3779B97F4A7C15ull ^ (uint64_t)inner * 0xBF58476D1CE4E5B9ull ^
+                 (uint64_t)outer * 0x94D049BB133111EBull ^ (uint64_t)o.ld * 31 ^ (uint64_t)box_outer;
+  ec_pipeline::TmapEntry &e = p->tmap_cache[(hsh >> 40) & 15];
+  if (e.ptr == o.ptr && e.inner == inner && e.outer == outer && e.batch == nb && e.ld == o.ld && e.stride == st &&
+      e.box_outer == box_outer) {
+    *tm = e.map;
+    return EC_OK;
+  }
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return fail(EC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3], strides[2];
+  cuuint32_t box[3], estr[3] = {1, 1, 1};
+  dims[0] = (cuuint64_t)inner;
+  dims[1] = (cuuint64_t)outer;
+  dims[2] = (cuuint64_t)nb;
+  strides[0] = (cuuint64_t)o.ld * 8;
+  // stride of the (possibly degenerate) batch dimension: any legal multiple of 16 when unused
+  strides[1] = batched ? (cuuint64_t)o.stride * 8 : (cuuint64_t)o.ld * 8 * (cuuint64_t)std::max<int64_t>(outer, 1);
+  box[0] = 16;
+  box[1] = (cuuint32_t)box_outer;
+  box[2] = 1;
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)o.ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(EC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  e.ptr = o.ptr; e.inner = inner; e.outer = outer; e.batch = nb; e.ld = o.ld; e.stride = st; e.box_outer = box_outer;
+  e.map = *tm;
+  return EC_OK;
+}
+
+constexpr size_t SK_WORKSPACE_BYTES = (size_t)640 * 128 * 128 * 8 / 4;  // >= grid * BM*BN*8 for every config
+constexpr int SK_MAX_GRID = 1024;
+
+int ensure_sk_workspace(ec_pipeline *p) {
+  if (p->sk_workspace) return EC_OK;
+  EC_CUDA(cudaMalloc((void **)&p->sk_workspace, SK_WORKSPACE_BYTES));
+  EC_CUDA(cudaMalloc((void **)&p->sk_flags, SK_MAX_GRID * sizeof(unsigned)));
+  EC_CUDA(cudaMemsetAsync(p->sk_flags, 0, SK_MAX_GRID * sizeof(unsigned), p->stream));
+  return EC_OK;
+}
+
+// Resident CTAs per SM of one kernel instantiation on one device (cached).
+template <class Cfg, bool AK, bool BK_>
+int ctas_per_sm(ec_pipeline *p, int *out) {
+  auto kern = ec::dgemm_tma_dmma_kernel<Cfg, AK, BK_>;
+  static std::atomic<int> cached[64];
+  int v = cached[p->device & 63].load();
+  if (v == 0) {
+    EC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int occ = 0;
+    EC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM_BYTES));
+    if (occ < 1) return fail(EC_ERR_CUDA, "kernel does not fit on an SM (occupancy 0)");
+    v = std::min(occ, Cfg::MIN_CTAS);
+    cached[p->device & 63].store(v);
+  }
+  *out = v;
+  return EC_OK;
+}
+
+template <class Cfg, bool AK, bool BK_>
+int launch_tma_dmma(ec_pipeline *p, const CUtensorMap &tmA, const CUtensorMap &tmB,
+                    ec::GemmParams &gp, bool want_sk) {
+  auto kern = ec::dgemm_tma_dmma_kernel<Cfg, AK, BK_>;
+  int ctas = 1;
+  int rc = ctas_per_sm<Cfg, AK, BK_>(p, &ctas);
+  if (rc) return rc;
+  const int64_t slots = (int64_t)(p->sm_count - p->sm_margin) * ctas;
+  const int64_t kblocks = (gp.K + ec::BK - 1) / ec::BK;
+  int grid = (int)std::min<int64_t>(gp.total_tiles, slots);
+  gp.sk_tiles = 0;
+  gp.sk_sms = p->sm_count - p->sm_margin;
+  gp.sk_workspace = nullptr;
+  gp.sk_flags = nullptr;
+  gp.sk_epoch = 0;
+  // Stream-K region: the tiles of the last, partial wave plus (when there is one) one full wave,
+  // so that every CTA gets between one and two tiles' worth of k-iterations in the region.
+  const int64_t rem = gp.total_tiles % slots;
+  if (want_sk && p->stream_k && (rem != 0 || getenv("EC_SK_ALL")) && slots <= SK_MAX_GRID &&
+      slots * (int64_t)(Cfg::BM * Cfg::BN * 8) <= (int64_t)SK_WORKSPACE_BYTES) {
+    int64_t sk_tiles = rem + (gp.total_tiles > slots ? slots : 0);
+    if (const char *e = getenv("EC_SK_ALL")) {   // experiment: stream-K over every tile
+      if (atoi(e)) sk_tiles = gp.total_tiles;
+    }
+    if (sk_tiles * kblocks >= 4 * slots) {   // at least 4 k-iterations per CTA in the region
+      rc = ensure_sk_workspace(p);
+      if (rc) return rc;
+      gp.sk_tiles = sk_tiles;
+      gp.sk_workspace = p->sk_workspace;
+      gp.sk_flags = p->sk_flags;
+      gp.sk_epoch = ++p->sk_epoch;
+      if (gp.sk_epoch == 0) gp.sk_epoch = ++p->sk_epoch;   // 0 is the cleared state
+      grid = (int)slots;
+    }
+  }
+  if (gp.sk_tiles == 0 && p->one_cta_per_tile && kblocks >= 64 && gp.total_tiles > slots)
+    grid = (int)std::min<int64_t>(gp.total_tiles, (int64_t)1 << 30);   // one tile per CTA
+  if (gp.sk_tiles > 0) {
+    // CTAs wait on one another's partials: a cooperative launch guarantees co-residency.
+    void *args[3] = {(void *)&tmA, (void *)&tmB, (void *)&gp};
+    EC_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(Cfg::THREADS), args,
+                                        (size_t)Cfg::SMEM_BYTES, p->stream));
+  } else {
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, p->stream>>>(tmA, tmB, gp);
+  }
+  EC_CUDA(cudaGetLastError());
+  p->launches++;
+  return EC_OK;
+}
+
+template <class Cfg>
+int run_tma_dmma(ec_pipeline *p, const Operand &oa, const Operand &ob, int64_t m, int64_t n,
+                 int64_t k, double alpha, double beta, double *C, int64_t ldc, int64_t stride_c,
+                 int64_t stride_a, int64_t stride_b, int64_t batch, bool want_sk,
+                 const char *const names[8]) {
+  CUtensorMap tmA, tmB;
+  int rc = make_tensor_map(p, &tmA, oa, batch, Cfg::BM);
+  if (rc) return rc;
+  rc = make_tensor_map(p, &tmB, ob, batch, Cfg::BN);
+  if (rc) return rc;
+  ec::GemmParams gp;
+  gp.M = m; gp.N = n; gp.K = k; gp.batch = batch;
+  gp.alpha = alpha; gp.beta = beta;
+  gp.C = C; gp.ldc = ldc; gp.stride_c = stride_c;
+  gp.tiles_m = (int)((m + Cfg::BM - 1) / Cfg::BM);
+  gp.tiles_n = (int)((n + Cfg::BN - 1) / Cfg::BN);
+  gp.total_tiles = (int64_t)gp.tiles_m * gp.tiles_n * batch;
+  gp.a_batched = (batch > 1 && stride_a != 0);
+  gp.b_batched = (batch > 1 && stride_b != 0);
+  gp.c_vec2 = (((uintptr_t)C & 15u) == 0 && (ldc & 1) == 0 && (batch <= 1 || (stride_c & 1) == 0)) ? 1 : 0;
+  int idx;
+  if (oa.kmajor && ob.kmajor) { idx = 0; rc = launch_tma_dmma<Cfg, true, true>(p, tmA, tmB, gp, want_sk); }
+  else if (oa.kmajor && !ob.kmajor) { idx = 1; rc = launch_tma_dmma<Cfg, true, false>(p, tmA, tmB, gp, want_sk); }
+  else if (!oa.kmajor && ob.kmajor) { idx = 2; rc = launch_tma_dmma<Cfg, false, true>(p, tmA, tmB, gp, want_sk); }
+  else { idx = 3; rc = launch_tma_dmma<Cfg, false, false>(p, tmA, tmB, gp, want_sk); }
+  p->last_kernel = names[idx + (gp.sk_tiles > 0 ? 4 : 0)];
+  return rc;
+}
+
+// Tile and schedule choice.  All configurations run the DMMA pipe at nearly the same rate once
+// it is fed; what differs is (a) load balance -- under the data-parallel schedule the busiest SM
+// does ceil(tiles / SMs) tiles, under stream-K every SM does tiles / SMs of them plus one
+// workspace round trip -- and (b) per-tile overhead and main-loop efficiency, which get worse
+// as tiles shrink.  Cost model in SM clocks, fitted to profiles/r01_tile_sweep*.json.
+enum { TILE_AUTO = 0, TILE_L = 1, TILE_S = 2, TILE_XS = 3 };
+
+struct TileChoice { int tile; bool sk; };
+
+TileChoice choose_tile(const ec_pipeline *p, int64_t m, int64_t n, int64_t k, int64_t batch) {
+  int force = 0;
+  bool allow_sk = p->stream_k != 0, force_sk = false;
+  // EC_FORCE_TILE=1..4 and EC_STREAM_K=0 (never) | 1 (cost model) | 2 (whenever feasible) override
+  // the choice for tools/tile_sweep.py and the tests; read per call
+  if (const char *e = getenv("EC_FORCE_TILE")) force = atoi(e);
+  if (const char *e = getenv("EC_STREAM_K")) {
+    allow_sk = atoi(e) != 0;
+    force_sk = atoi(e) == 2;
+  }
+  // eff[r-1]: fraction of the DMMA issue rate the main loop sustains with r CTAs resident per SM
+  // (the 4-warp tiles put one warp on each SM sub-partition per CTA and hide their LDS latency
+  // badly until a second or third CTA shares the SM); overhead: exposed clocks per tile; fixup:
+  // exposed clocks of one stream-K tail (publish partial, wait, read, epilogue).  Fitted to
+  // profiles/r01_tile_sweep*.json and profiles/r01_small_probe.txt (back-to-back launches).
+  struct Cand { int id, bm, bn, ctas; double eff[3], overhead, fixup; };
+  const Cand cands[3] = {{TILE_L, 128, 128, 1, {0.987, 0.987, 0.987}, 2300.0, 30000.0},
+                         {TILE_S, 64, 64, 2, {0.59, 0.955, 0.955}, 1200.0, 17000.0},
+                         {TILE_XS, 64, 32, 3, {0.50, 0.76, 0.80}, 800.0, 20000.0}};
+  const double kpad = (double)((k + 15) / 16 * 16);
+  const int64_t kblocks = (k + 15) / 16;
+  double best = 1e300;
+  TileChoice pick{TILE_L, false};
+  for (const Cand &c : cands) {
+    if (force >= TILE_L && force <= TILE_XS && c.id != force) continue;
+    const int64_t tiles = ((m + c.bm - 1) / c.bm) * ((n + c.bn - 1) / c.bn) * batch;
+    const int sms = p->sm_count - p->sm_margin;
+    const int64_t slots = (int64_t)sms * c.ctas;
+    const int64_t resident = std::max<int64_t>(1, std::min<int64_t>(c.ctas, (tiles + sms - 1) / sms));
+    const double tile_clk = (double)c.bm * c.bn * kpad / 64.0 / c.eff[resident - 1] + c.overhead;
+    const double dp = (double)((tiles + sms - 1) / sms) * tile_clk;
+    if (dp < best) { best = dp; pick = {c.id, false}; }
+    const int64_t rem = tiles % slots;
+    const int64_t sk_tiles = rem + (tiles > slots ? slots : 0);
+    if (allow_sk && rem != 0 && sk_tiles * kblocks >= 4 * slots) {
+      // every SM does its exact share; one partial tile written and one read per CTA
+      // the stream-K grid fills every slot, so the SM runs at its full-occupancy efficiency
+      const double tile_clk_sk = (double)c.bm * c.bn * kpad / 64.0 / c.eff[c.ctas - 1] + c.overhead;
+      // with far fewer tiles than CTAs a tile is cut into several partials and its owner adds
+      // them one after the other: the exposed tail grows with the partials per tile
+      const double splits = std::max(1.0, (double)slots / (double)tiles);
+      const double sk = force_sk ? dp * 1e-3
+                                 : (double)tiles / sms * tile_clk_sk + c.fixup * (1.0 + 0.35 * (splits - 1.0));
+      if (sk < best) { best = sk; pick = {c.id, true}; }
+    }
+  }
+  return pick;
+}
+
+
+
+}  // namespace

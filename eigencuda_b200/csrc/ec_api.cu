@@ -25,931 +25,14 @@
 #include "dgemm_kernels.cuh"
 #include "ozaki_kernels.cuh"
 
-// ------------------------------------------------------------------------------------------
-// errors
-// ------------------------------------------------------------------------------------------
-namespace {
 
-thread_local std::string g_last_error;
-
-int fail(int code, const char *fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof(buf), fmt, ap);
-  va_end(ap);
-  g_last_error = buf;
-  return code;
-}
-
-#define EC_CUDA(call)                                                                        \
-  do {                                                                                       \
-    cudaError_t _e = (call);                                                                 \
-    if (_e != cudaSuccess)                                                                   \
-      return fail(EC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e),       \
-                  __FILE__, __LINE__);                                                       \
-  } while (0)
-
-// ------------------------------------------------------------------------------------------
-// driver entry point for tensor-map encoding (no link-time dependency on libcuda, so the
-// library loads -- and its symbols can be checked -- on a machine without a GPU driver)
-// ------------------------------------------------------------------------------------------
-typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
-                                    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-encode_tiled_fn get_encode_tiled() {
-  static encode_tiled_fn fn = []() -> encode_tiled_fn {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) !=
-            cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<encode_tiled_fn>(p);
-  }();
-  return fn;
-}
-
-// ------------------------------------------------------------------------------------------
-// pinned staging ring: lets a pageable source be released to the caller as soon as
-// copy_to_gpu returns (the reference's observable contract, src/cudamatrix.cc:47-51) while the
-// DMA itself runs asynchronously from pinned memory.
-// ------------------------------------------------------------------------------------------
-struct StagingRing {
-  static constexpr int SLOTS = 4;
-  void *buf[SLOTS] = {};
-  size_t cap[SLOTS] = {};
-  cudaEvent_t ev[SLOTS] = {};
-  bool busy[SLOTS] = {};
-  int next = 0;
-
-  // Returns a pinned buffer of at least `bytes`, free for the host to write.
-  int acquire(size_t bytes, int *slot) {
-    int s = next;
-    next = (next + 1) % SLOTS;
-    if (!ev[s]) EC_CUDA(cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming));
-    if (busy[s]) {
-      EC_CUDA(cudaEventSynchronize(ev[s]));
-      busy[s] = false;
-    }
-    if (cap[s] < bytes) {
-      if (buf[s]) EC_CUDA(cudaFreeHost(buf[s]));
-      buf[s] = nullptr;
-      cap[s] = 0;
-      size_t want = std::max(bytes, (size_t)1 << 20);
-      EC_CUDA(cudaHostAlloc(&buf[s], want, cudaHostAllocDefault));
-      cap[s] = want;
-    }
-    *slot = s;
-    return EC_OK;
-  }
-  int release_after(int s, cudaStream_t st) {
-    EC_CUDA(cudaEventRecord(ev[s], st));
-    busy[s] = true;
-    return EC_OK;
-  }
-  void destroy() {
-    for (int s = 0; s < SLOTS; ++s) {
-      if (busy[s]) cudaEventSynchronize(ev[s]);
-      if (ev[s]) cudaEventDestroy(ev[s]);
-      if (buf[s]) cudaFreeHost(buf[s]);
-      ev[s] = nullptr;
-      buf[s] = nullptr;
-      cap[s] = 0;
-      busy[s] = false;
-    }
-  }
-};
-
-bool is_pinned_host(const void *p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  return a.type == cudaMemoryTypeHost;
-}
-bool is_device_ptr(const void *p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
-}
-
-// Small persistent worker pool for pageable <-> pinned staging copies.
-class CopyPool {
- public:
-  explicit CopyPool(int n) : stop_(false), pending_(0) {
-    for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
-  }
-  ~CopyPool() {
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      stop_ = true;
-    }
-    cv_.notify_all();
-    for (auto &t : workers_) t.join();
-  }
-  int size() const { return (int)workers_.size(); }
-  // Run fn(i) for i in [0, n) on the pool and wait.
-  void parallel_for(int64_t n, const std::function<void(int64_t)> &fn) {
-    if (n <= 0) return;
-    if (workers_.empty()) {
-      for (int64_t i = 0; i < n; ++i) fn(i);
-      return;
-    }
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      fn_ = &fn;
-      next_ = 0;
-      end_ = n;
-      pending_ = n;
-    }
-    cv_.notify_all();
-    std::unique_lock<std::mutex> lk(mu_);
-    done_cv_.wait(lk, [this] { return pending_ == 0; });
-    fn_ = nullptr;
-  }
-
- private:
-  void run() {
-    std::unique_lock<std::mutex> lk(mu_);
-    for (;;) {
-      cv_.wait(lk, [this] { return stop_ || (fn_ && next_ < end_); });
-      if (stop_) return;
-      while (fn_ && next_ < end_) {
-        int64_t i = next_++;
-        const std::function<void(int64_t)> *f = fn_;
-        lk.unlock();
-        (*f)(i);
-        lk.lock();
-        if (--pending_ == 0) done_cv_.notify_all();
-      }
-    }
-  }
-  std::vector<std::thread> workers_;
-  std::mutex mu_;
-  std::condition_variable cv_, done_cv_;
-  bool stop_;
-  const std::function<void(int64_t)> *fn_ = nullptr;
-  int64_t next_ = 0, end_ = 0, pending_;
-};
-
-}  // namespace
-
-// ------------------------------------------------------------------------------------------
-// handles
-// ------------------------------------------------------------------------------------------
-struct StreamEngine;
-
-struct ec_pipeline {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  bool owns_stream = true;
-  int backend = EC_BACKEND_FP64_DMMA;
-  int sm_count = 0;
-  int64_t launches = 0;
-  const char *last_kernel = "none";
-  StagingRing staging;
-  StreamEngine *engine = nullptr;
-  int cfg_chunk = 0, cfg_ring = 0, cfg_threads = 0;
-  // stream-K fix-up workspace (partial accumulator tiles + flags), allocated on first use
-  double *sk_workspace = nullptr;
-  unsigned *sk_flags = nullptr;
-  unsigned sk_epoch = 0;
-  int stream_k = 1;   // 0 disables the stream-K schedule (EC_STREAM_K=0)
-  int sm_margin = 0;  // SMs left free for concurrent kernels (NCCL during SUMMA)
-  int one_cta_per_tile = 0;  // non-persistent launch for long tiles (shared-GPU friendly)
-  // small direct-mapped cache of encoded tensor maps: the compat loop and every tensor-stream
-  // chunk reuse the same few device buffers, and cuTensorMapEncodeTiled costs about a microsecond
-  struct TmapEntry {
-    const void *ptr = nullptr;
-    int64_t inner = 0, outer = 0, batch = 0, ld = 0, stride = 0;
-    int box_outer = 0;
-    CUtensorMap map;
-  } tmap_cache[16];
-  // EC_BACKEND_OZAKI_I8 workspace: digit planes and row/column scales, grown on demand
-  int8_t *oz_planes_a = nullptr, *oz_planes_b = nullptr;
-  double *oz_scale_a = nullptr, *oz_scale_b = nullptr;
-  unsigned long long *oz_amax = nullptr;
-  size_t oz_planes_a_bytes = 0, oz_planes_b_bytes = 0, oz_scale_a_bytes = 0, oz_scale_b_bytes = 0, oz_amax_bytes = 0;
-  cudaStream_t oz_split_stream = nullptr;          // splits of chunk c+1 overlap the GEMM of chunk c
-  cudaEvent_t oz_ev_split[2] = {nullptr, nullptr}, oz_ev_gemm[2] = {nullptr, nullptr};
-};
-
-struct ec_matrix {
-  double *data = nullptr;
-  int64_t rows = 0, cols = 0;
-  cudaStream_t stream = nullptr;
-  int device = 0;
-};
-
-namespace {
-
-// stream -> pipeline registry, so that CudaMatrix (which only knows its stream, reference
-// include/cudamatrix.hpp:57) can find its pipeline's staging ring.
-std::mutex g_registry_mu;
-std::unordered_map<void *, ec_pipeline *> g_registry;
-
-ec_pipeline *pipeline_of_stream(cudaStream_t s) {
-  std::lock_guard<std::mutex> lk(g_registry_mu);
-  auto it = g_registry.find((void *)s);
-  return it == g_registry.end() ? nullptr : it->second;
-}
-
-struct DeviceGuard {
-  int prev = -1;
-  bool active = false;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
-      cudaSetDevice(dev);
-      active = true;
-    }
-  }
-  ~DeviceGuard() {
-    if (active) cudaSetDevice(prev);
-  }
-};
-
-// ------------------------------------------------------------------------------------------
-// kernel dispatch
-// ------------------------------------------------------------------------------------------
-struct Operand {
-  const double *ptr;
-  int64_t ld, stride;
-  bool kmajor;     // contiguous along k
-  int64_t mn, k;   // extents of op(X): mn x k
-};
-
-bool tma_ok(const Operand &o, int64_t batch) {
-  if (((uintptr_t)o.ptr & 15u) != 0) return false;
-  if ((o.ld & 1) != 0) return false;                       // row pitch must be a multiple of 16 B
-  if (batch > 1 && o.stride != 0 && (o.stride & 1) != 0) return false;
-  if (o.mn >= ((int64_t)1 << 31) || o.k >= ((int64_t)1 << 31)) return false;
-  if (o.ld * 8 >= ((int64_t)1 << 40) || o.stride * 8 >= ((int64_t)1 << 40)) return false;
-  return true;
-}
-
-int make_tensor_map(ec_pipeline *p, CUtensorMap *tm, const Operand &o, int64_t batch, int tile_extent) {
-  const bool batched = batch > 1 && o.stride != 0;
-  const int64_t inner = o.kmajor ? o.k : o.mn, outer = o.kmajor ? o.mn : o.k;
-  const int box_outer = o.kmajor ? tile_extent : ec::BK;
-  const int64_t nb = batched ? batch : 1, st = batched ? o.stride : 0;
-  // cache lookup
-  uint64_t hsh = (uint64_t)(uintptr_t)o.ptr * 0x9E3779B97F4A7C15ull ^ (uint64_t)inner * 0xBF58476D1CE4E5B9ull ^
-                 (uint64_t)outer * 0x94D049BB133111EBull ^ (uint64_t)o.ld * 31 ^ (uint64_t)box_outer;
-  ec_pipeline::TmapEntry &e = p->tmap_cache[(hsh >> 40) & 15];
-  if (e.ptr == o.ptr && e.inner == inner && e.outer == outer && e.batch == nb && e.ld == o.ld && e.stride == st &&
-      e.box_outer == box_outer) {
-    *tm = e.map;
-    return EC_OK;
-  }
-  encode_tiled_fn enc = get_encode_tiled();
-  if (!enc) return fail(EC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t dims[3], strides[2];
-  cuuint32_t box[3], estr[3] = {1, 1, 1};
-  dims[0] = (cuuint64_t)inner;
-  dims[1] = (cuuint64_t)outer;
-  dims[2] = (cuuint64_t)nb;
-  strides[0] = (cuuint64_t)o.ld * 8;
-  // stride of the (possibly degenerate) batch dimension: any legal multiple of 16 when unused
-  strides[1] = batched ? (cuuint64_t)o.stride * 8 : (cuuint64_t)o.ld * 8 * (cuuint64_t)std::max<int64_t>(outer, 1);
-  box[0] = 16;
-  box[1] = (cuuint32_t)box_outer;
-  box[2] = 1;
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)o.ptr, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return fail(EC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  e.ptr = o.ptr; e.inner = inner; e.outer = outer; e.batch = nb; e.ld = o.ld; e.stride = st; e.box_outer = box_outer;
-  e.map = *tm;
-  return EC_OK;
-}
-
-constexpr size_t SK_WORKSPACE_BYTES = (size_t)640 * 128 * 128 * 8 / 4;  // >= grid * BM*BN*8 for every config
-constexpr int SK_MAX_GRID = 1024;
-
-int ensure_sk_workspace(ec_pipeline *p) {
-  if (p->sk_workspace) return EC_OK;
-  EC_CUDA(cudaMalloc((void **)&p->sk_workspace, SK_WORKSPACE_BYTES));
-  EC_CUDA(cudaMalloc((void **)&p->sk_flags, SK_MAX_GRID * sizeof(unsigned)));
-  EC_CUDA(cudaMemsetAsync(p->sk_flags, 0, SK_MAX_GRID * sizeof(unsigned), p->stream));
-  return EC_OK;
-}
-
-// Resident CTAs per SM of one kernel instantiation on one device (cached).
-template <class Cfg, bool AK, bool BK_>
-int ctas_per_sm(ec_pipeline *p, int *out) {
-  auto kern = ec::dgemm_tma_dmma_kernel<Cfg, AK, BK_>;
-  static std::atomic<int> cached[64];
-  int v = cached[p->device & 63].load();
-  if (v == 0) {
-    EC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    int occ = 0;
-    EC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM_BYTES));
-    if (occ < 1) return fail(EC_ERR_CUDA, "kernel does not fit on an SM (occupancy 0)");
-    v = std::min(occ, Cfg::MIN_CTAS);
-    cached[p->device & 63].store(v);
-  }
-  *out = v;
-  return EC_OK;
-}
-
-template <class Cfg, bool AK, bool BK_>
-int launch_tma_dmma(ec_pipeline *p, const CUtensorMap &tmA, const CUtensorMap &tmB,
-                    ec::GemmParams &gp, bool want_sk) {
-  auto kern = ec::dgemm_tma_dmma_kernel<Cfg, AK, BK_>;
-  int ctas = 1;
-  int rc = ctas_per_sm<Cfg, AK, BK_>(p, &ctas);
-  if (rc) return rc;
-  const int64_t slots = (int64_t)(p->sm_count - p->sm_margin) * ctas;
-  const int64_t kblocks = (gp.K + ec::BK - 1) / ec::BK;
-  int grid = (int)std::min<int64_t>(gp.total_tiles, slots);
-  gp.sk_tiles = 0;
-  gp.sk_sms = p->sm_count - p->sm_margin;
-  gp.sk_workspace = nullptr;
-  gp.sk_flags = nullptr;
-  gp.sk_epoch = 0;
-  // Stream-K region: the tiles of the last, partial wave plus (when there is one) one full wave,
-  // so that every CTA gets between one and two tiles' worth of k-iterations in the region.
-  const int64_t rem = gp.total_tiles % slots;
-  if (want_sk && p->stream_k && (rem != 0 || getenv("EC_SK_ALL")) && slots <= SK_MAX_GRID &&
-      slots * (int64_t)(Cfg::BM * Cfg::BN * 8) <= (int64_t)SK_WORKSPACE_BYTES) {
-    int64_t sk_tiles = rem + (gp.total_tiles > slots ? slots : 0);
-    if (const char *e = getenv("EC_SK_ALL")) {   // experiment: stream-K over every tile
-      if (atoi(e)) sk_tiles = gp.total_tiles;
-    }
-    if (sk_tiles * kblocks >= 4 * slots) {   // at least 4 k-iterations per CTA in the region
-      rc = ensure_sk_workspace(p);
-      if (rc) return rc;
-      gp.sk_tiles = sk_tiles;
-      gp.sk_workspace = p->sk_workspace;
-      gp.sk_flags = p->sk_flags;
-      gp.sk_epoch = ++p->sk_epoch;
-      if (gp.sk_epoch == 0) gp.sk_epoch = ++p->sk_epoch;   // 0 is the cleared state
-      grid = (int)slots;
-    }
-  }
-  if (gp.sk_tiles == 0 && p->one_cta_per_tile && kblocks >= 64 && gp.total_tiles > slots)
-    grid = (int)std::min<int64_t>(gp.total_tiles, (int64_t)1 << 30);   // one tile per CTA
-  if (gp.sk_tiles > 0) {
-    // CTAs wait on one another's partials: a cooperative launch guarantees co-residency.
-    void *args[3] = {(void *)&tmA, (void *)&tmB, (void *)&gp};
-    EC_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(Cfg::THREADS), args,
-                                        (size_t)Cfg::SMEM_BYTES, p->stream));
-  } else {
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, p->stream>>>(tmA, tmB, gp);
-  }
-  EC_CUDA(cudaGetLastError());
-  p->launches++;
-  return EC_OK;
-}
-
-template <class Cfg>
-int run_tma_dmma(ec_pipeline *p, const Operand &oa, const Operand &ob, int64_t m, int64_t n,
-                 int64_t k, double alpha, double beta, double *C, int64_t ldc, int64_t stride_c,
-                 int64_t stride_a, int64_t stride_b, int64_t batch, bool want_sk,
-                 const char *const names[8]) {
-  CUtensorMap tmA, tmB;
-  int rc = make_tensor_map(p, &tmA, oa, batch, Cfg::BM);
-  if (rc) return rc;
-  rc = make_tensor_map(p, &tmB, ob, batch, Cfg::BN);
-  if (rc) return rc;
-  ec::GemmParams gp;
-  gp.M = m; gp.N = n; gp.K = k; gp.batch = batch;
-  gp.alpha = alpha; gp.beta = beta;
-  gp.C = C; gp.ldc = ldc; gp.stride_c = stride_c;
-  gp.tiles_m = (int)((m + Cfg::BM - 1) / Cfg::BM);
-  gp.tiles_n = (int)((n + Cfg::BN - 1) / Cfg::BN);
-  gp.total_tiles = (int64_t)gp.tiles_m * gp.tiles_n * batch;
-  gp.a_batched = (batch > 1 && stride_a != 0);
-  gp.b_batched = (batch > 1 && stride_b != 0);
-  gp.c_vec2 = (((uintptr_t)C & 15u) == 0 && (ldc & 1) == 0 && (batch <= 1 || (stride_c & 1) == 0)) ? 1 : 0;
-  int idx;
-  if (oa.kmajor && ob.kmajor) { idx = 0; rc = launch_tma_dmma<Cfg, true, true>(p, tmA, tmB, gp, want_sk); }
-  else if (oa.kmajor && !ob.kmajor) { idx = 1; rc = launch_tma_dmma<Cfg, true, false>(p, tmA, tmB, gp, want_sk); }
-  else if (!oa.kmajor && ob.kmajor) { idx = 2; rc = launch_tma_dmma<Cfg, false, true>(p, tmA, tmB, gp, want_sk); }
-  else { idx = 3; rc = launch_tma_dmma<Cfg, false, false>(p, tmA, tmB, gp, want_sk); }
-  p->last_kernel = names[idx + (gp.sk_tiles > 0 ? 4 : 0)];
-  return rc;
-}
-
-// Tile and schedule choice.  All configurations run the DMMA pipe at nearly the same rate once
-// it is fed; what differs is (a) load balance -- under the data-parallel schedule the busiest SM
-// does ceil(tiles / SMs) tiles, under stream-K every SM does tiles / SMs of them plus one
-// workspace round trip -- and (b) per-tile overhead and main-loop efficiency, which get worse
-// as tiles shrink.  Cost model in SM clocks, fitted to profiles/r01_tile_sweep*.json.
-enum { TILE_AUTO = 0, TILE_L = 1, TILE_S = 2, TILE_XS = 3 };
-
-struct TileChoice { int tile; bool sk; };
-
-TileChoice choose_tile(const ec_pipeline *p, int64_t m, int64_t n, int64_t k, int64_t batch) {
-  int force = 0;
-  bool allow_sk = p->stream_k != 0, force_sk = false;
-  // EC_FORCE_TILE=1..4 and EC_STREAM_K=0 (never) | 1 (cost model) | 2 (whenever feasible) override
-  // the choice for tools/tile_sweep.py and the tests; read per call
-  if (const char *e = getenv("EC_FORCE_TILE")) force = atoi(e);
-  if (const char *e = getenv("EC_STREAM_K")) {
-    allow_sk = atoi(e) != 0;
-    force_sk = atoi(e) == 2;
-  }
-  // eff[r-1]: fraction of the DMMA issue rate the main loop sustains with r CTAs resident per SM
-  // (the 4-warp tiles put one warp on each SM sub-partition per CTA and hide their LDS latency
-  // badly until a second or third CTA shares the SM); overhead: exposed clocks per tile; fixup:
-  // exposed clocks of one stream-K tail (publish partial, wait, read, epilogue).  Fitted to
-  // profiles/r01_tile_sweep*.json and profiles/r01_small_probe.txt (back-to-back launches).
-  struct Cand { int id, bm, bn, ctas; double eff[3], overhead, fixup; };
-  const Cand cands[3] = {{TILE_L, 128, 128, 1, {0.987, 0.987, 0.987}, 2300.0, 30000.0},
-                         {TILE_S, 64, 64, 2, {0.59, 0.955, 0.955}, 1200.0, 17000.0},
-                         {TILE_XS, 64, 32, 3, {0.50, 0.76, 0.80}, 800.0, 20000.0}};
-  const double kpad = (double)((k + 15) / 16 * 16);
-  const int64_t kblocks = (k + 15) / 16;
-  double best = 1e300;
-  TileChoice pick{TILE_L, false};
-  for (const Cand &c : cands) {
-    if (force >= TILE_L && force <= TILE_XS && c.id != force) continue;
-    const int64_t tiles = ((m + c.bm - 1) / c.bm) * ((n + c.bn - 1) / c.bn) * batch;
-    const int sms = p->sm_count - p->sm_margin;
-    const int64_t slots = (int64_t)sms * c.ctas;
-    const int64_t resident = std::max<int64_t>(1, std::min<int64_t>(c.ctas, (tiles + sms - 1) / sms));
-    const double tile_clk = (double)c.bm * c.bn * kpad / 64.0 / c.eff[resident - 1] + c.overhead;
-    const double dp = (double)((tiles + sms - 1) / sms) * tile_clk;
-    if (dp < best) { best = dp; pick = {c.id, false}; }
-    const int64_t rem = tiles % slots;
-    const int64_t sk_tiles = rem + (tiles > slots ? slots : 0);
-    if (allow_sk && rem != 0 && sk_tiles * kblocks >= 4 * slots) {
-      // every SM does its exact share; one partial tile written and one read per CTA
-      // the stream-K grid fills every slot, so the SM runs at its full-occupancy efficiency
-      const double tile_clk_sk = (double)c.bm * c.bn * kpad / 64.0 / c.eff[c.ctas - 1] + c.overhead;
-      // with far fewer tiles than CTAs a tile is cut into several partials and its owner adds
-      // them one after the other: the exposed tail grows with the partials per tile
-      const double splits = std::max(1.0, (double)slots / (double)tiles);
-      const double sk = force_sk ? dp * 1e-3
-                                 : (double)tiles / sms * tile_clk_sk + c.fixup * (1.0 + 0.35 * (splits - 1.0));
-      if (sk < best) { best = sk; pick = {c.id, true}; }
-    }
-  }
-  return pick;
-}
-
-
-// ------------------------------------------------------------------------------------------
-// EC_BACKEND_OZAKI_I8: FP64 product emulated on the int8 tensor cores (ozaki_kernels.cuh)
-// ------------------------------------------------------------------------------------------
-constexpr int OZ_S = 7;   // digit planes: 49 fractional bits below each row/column maximum
-
-// Shapes the emulation takes; everything else runs the native FP64 kernels (which are at least
-// as accurate).  K <= 65536 keeps the int32 accumulators exact for 7 planes.
-constexpr int64_t OZ_MAX_K = 65536;   // 7 * 65536 * 65^2 < 2^31: deeper products are cut along k
-bool ozaki_eligible(int64_t m, int64_t n, int64_t k) {
-  return k >= 64 && m >= 64 && n >= 32 && m * n * k >= (int64_t)128 * 128 * 128 &&
-         m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31);
-}
-
-template <class T>
-int oz_grow(T **buf, size_t *have, size_t want) {
-  if (want <= *have) return EC_OK;
-  if (*buf) EC_CUDA(cudaFree(*buf));
-  *buf = nullptr;
-  *have = 0;
-  EC_CUDA(cudaMalloc((void **)buf, want));
-  *have = want;
-  return EC_OK;
-}
-
-int oz_tensor_map(CUtensorMap *tm, const int8_t *planes, int64_t K, int64_t Kp, int64_t R, int64_t batch,
-                  int box_rows) {
-  encode_tiled_fn enc = get_encode_tiled();
-  if (!enc) return fail(EC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)R, (cuuint64_t)OZ_S, (cuuint64_t)std::max<int64_t>(batch, 1)};
-  cuuint64_t strides[3] = {(cuuint64_t)Kp, (cuuint64_t)(R * Kp), (cuuint64_t)(OZ_S * R * Kp)};
-  cuuint32_t box[4] = {(cuuint32_t)ec::oz::OBK, (cuuint32_t)box_rows, (cuuint32_t)OZ_S, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)planes, dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(EC_ERR_CUDA, "cuTensorMapEncodeTiled (int8 planes) failed with CUresult %d", (int)r);
-  return EC_OK;
-}
-
-// Scale + split one operand: op(X) viewed as R rows x K, element (r, q) at X[r*rs + q*ks].
-// `amax` is scratch for R*batch abs-max bit patterns.
-int oz_split(ec_pipeline *p, const double *X, int64_t rs, int64_t ks, int64_t bstride, int64_t R, int64_t K,
-             int64_t Kp, int64_t batch, int8_t *planes, double *scale, unsigned long long *amax) {
-  ec::oz::SplitParams sp{X, rs, ks, bstride, R, K, Kp, batch, planes, scale};
-  const bool row_contig = (rs == 1 && ks != 1);
-  EC_CUDA(cudaMemsetAsync(amax, 0, (size_t)(R * batch) * 8, p->stream));
-  const int64_t rt = (R + ec::oz::SPLIT_ROWS - 1) / ec::oz::SPLIT_ROWS;
-  const int64_t tiles_k = ((K + ec::oz::SPLIT_K - 1) / ec::oz::SPLIT_K) * rt * batch;
-  const int64_t tiles_kp = ((Kp + ec::oz::SPLIT_K - 1) / ec::oz::SPLIT_K) * rt * batch;
-  const int g1 = (int)std::min<int64_t>(tiles_k, (int64_t)p->sm_count * 8);
-  const int g2 = (int)std::min<int64_t>(tiles_kp, (int64_t)p->sm_count * 8);
-  if (row_contig) {
-    ec::oz::ozaki_absmax_kernel<true><<<g1, ec::oz::SPLIT_THREADS, 0, p->stream>>>(sp, amax);
-    ec::oz::ozaki_split_kernel<OZ_S, true><<<g2, ec::oz::SPLIT_THREADS, 0, p->stream>>>(sp, amax);
-  } else {
-    ec::oz::ozaki_absmax_kernel<false><<<g1, ec::oz::SPLIT_THREADS, 0, p->stream>>>(sp, amax);
-    ec::oz::ozaki_split_kernel<OZ_S, false><<<g2, ec::oz::SPLIT_THREADS, 0, p->stream>>>(sp, amax);
-  }
-  EC_CUDA(cudaGetLastError());
-  p->launches += 2;
-  return EC_OK;
-}
-
-int ozaki_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha,
-                   const double *A, int64_t lda, int64_t stride_a, const double *B, int64_t ldb, int64_t stride_b,
-                   double beta, double *C, int64_t ldc, int64_t stride_c, int64_t batch) {
-  using Cfg = ec::oz::OzCfg<OZ_S>;
-  const int64_t Kp = (k + 15) / 16 * 16;
-  const bool a_batched = batch > 1 && stride_a != 0, b_batched = batch > 1 && stride_b != 0;
-  // chunk the batch so that the digit planes of a chunk stay around L2 size; the batched
-  // operand(s) are double-buffered so that the split of chunk c+1 (LSU / FP64 pipe / HBM) runs on
-  // a side stream underneath the GEMM of chunk c (tensor cores / L2)
-  const int64_t per_problem = OZ_S * Kp * ((a_batched ? m : 0) + (b_batched ? n : 0));
-  int64_t chunk = batch;
-  if (per_problem > 0) chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t)192 << 20) / per_problem));
-  if (const char *e = getenv("EC_OZAKI_CHUNK")) chunk = std::max<int64_t>(1, std::min<int64_t>(batch, atoll(e)));
-  const int64_t nchunks = (batch + chunk - 1) / chunk;
-  const bool pipelined = nchunks > 1 && (a_batched || b_batched);
-  const int nbuf = pipelined ? 2 : 1;
-  const int64_t ca = a_batched ? chunk : 1, cb = b_batched ? chunk : 1;
-  const size_t pa = (size_t)(OZ_S * m * Kp * ca), pb = (size_t)(OZ_S * n * Kp * cb);
-  const size_t sa_b = (size_t)(m * ca * 8), sb_b = (size_t)(n * cb * 8), am_b = (size_t)(std::max(m * ca, n * cb) * 8);
-  int rc;
-  if ((rc = oz_grow(&p->oz_planes_a, &p->oz_planes_a_bytes, pa * (a_batched ? nbuf : 1)))) return rc;
-  if ((rc = oz_grow(&p->oz_planes_b, &p->oz_planes_b_bytes, pb * (b_batched ? nbuf : 1)))) return rc;
-  if ((rc = oz_grow(&p->oz_scale_a, &p->oz_scale_a_bytes, sa_b * (a_batched ? nbuf : 1)))) return rc;
-  if ((rc = oz_grow(&p->oz_scale_b, &p->oz_scale_b_bytes, sb_b * (b_batched ? nbuf : 1)))) return rc;
-  if ((rc = oz_grow(&p->oz_amax, &p->oz_amax_bytes, am_b * 3))) return rc;   // [shared operand, buffer 0, buffer 1]
-  if (pipelined && !p->oz_split_stream) {
-    EC_CUDA(cudaStreamCreateWithFlags(&p->oz_split_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      EC_CUDA(cudaEventCreateWithFlags(&p->oz_ev_split[i], cudaEventDisableTiming));
-      EC_CUDA(cudaEventCreateWithFlags(&p->oz_ev_gemm[i], cudaEventDisableTiming));
-    }
-  }
-  auto kern = ec::oz::ozaki_gemm_kernel<OZ_S>;
-  static std::atomic<uint64_t> configured{0};
-  const uint64_t bit = 1ull << (p->device & 63);
-  if (!(configured.load() & bit)) {
-    EC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured.fetch_or(bit);
-  }
-  // op(A)(r, q): N -> A[r + q*lda]; T -> A[r*lda + q].  op(B)^T(j, q) = op(B)(q, j): N -> B[j*ldb + q]; T -> B[q*ldb + j]
-  const int64_t a_rs = transa ? lda : 1, a_ks = transa ? 1 : lda;
-  const int64_t b_rs = transb ? 1 : ldb, b_ks = transb ? ldb : 1;
-  unsigned long long *amax_shared = p->oz_amax, *amax_buf[2] = {p->oz_amax + am_b / 8, p->oz_amax + 2 * (am_b / 8)};
-  if (!a_batched && (rc = oz_split(p, A, a_rs, a_ks, 0, m, k, Kp, 1, p->oz_planes_a, p->oz_scale_a, amax_shared))) return rc;
-  if (!b_batched && (rc = oz_split(p, B, b_rs, b_ks, 0, n, k, Kp, 1, p->oz_planes_b, p->oz_scale_b, amax_shared))) return rc;
-
-  cudaStream_t main_stream = p->stream;
-  // split of chunk c into buffer c & 1, on the side stream when pipelined
-  auto split_chunk = [&](int64_t c) -> int {
-    const int64_t b0 = c * chunk, nb = std::min(chunk, batch - b0);
-    const int buf = pipelined ? (int)(c & 1) : 0;
-    if (pipelined) {
-      p->stream = p->oz_split_stream;
-      if (c >= 2) EC_CUDA(cudaStreamWaitEvent(p->oz_split_stream, p->oz_ev_gemm[buf], 0));   // buffer consumed
-    }
-    int r = EC_OK;
-    if (a_batched)
-      r = oz_split(p, A + b0 * stride_a, a_rs, a_ks, stride_a, m, k, Kp, nb, p->oz_planes_a + buf * pa,
-                   p->oz_scale_a + buf * (sa_b / 8), amax_buf[buf]);
-    if (!r && b_batched)
-      r = oz_split(p, B + b0 * stride_b, b_rs, b_ks, stride_b, n, k, Kp, nb, p->oz_planes_b + buf * pb,
-                   p->oz_scale_b + buf * (sb_b / 8), amax_buf[buf]);
-    if (pipelined) {
-      if (!r) {
-        cudaError_t e = cudaEventRecord(p->oz_ev_split[buf], p->oz_split_stream);
-        if (e != cudaSuccess) r = fail(EC_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
-      }
-      p->stream = main_stream;
-    }
-    return r;
-  };
-  if (pipelined) {
-    // the side stream starts after whatever produced the operands on the main stream
-    EC_CUDA(cudaEventRecord(p->oz_ev_gemm[0], main_stream));
-    EC_CUDA(cudaStreamWaitEvent(p->oz_split_stream, p->oz_ev_gemm[0], 0));
-  }
-  if (a_batched || b_batched) {
-    if ((rc = split_chunk(0))) { p->stream = main_stream; return rc; }
-  }
-  for (int64_t c = 0; c < nchunks; ++c) {
-    const int64_t b0 = c * chunk, nb = std::min(chunk, batch - b0);
-    const int buf = pipelined ? (int)(c & 1) : 0;
-    if (pipelined && c + 1 < nchunks && (rc = split_chunk(c + 1))) { p->stream = main_stream; return rc; }
-    if (!pipelined && c > 0 && (a_batched || b_batched) && (rc = split_chunk(c))) return rc;
-    if (pipelined) EC_CUDA(cudaStreamWaitEvent(main_stream, p->oz_ev_split[buf], 0));
-    CUtensorMap tmA, tmB;
-    if ((rc = oz_tensor_map(&tmA, p->oz_planes_a + (a_batched ? buf * pa : 0), k, Kp, m, a_batched ? nb : 1, ec::oz::OM))) return rc;
-    if ((rc = oz_tensor_map(&tmB, p->oz_planes_b + (b_batched ? buf * pb : 0), k, Kp, n, b_batched ? nb : 1, ec::oz::ON))) return rc;
-    ec::oz::GemmOzParams gp;
-    gp.M = m; gp.N = n; gp.K = k; gp.batch = nb;
-    gp.alpha = alpha; gp.beta = beta;
-    gp.C = C + b0 * stride_c; gp.ldc = ldc; gp.stride_c = stride_c;
-    gp.sa = p->oz_scale_a + (a_batched ? buf * (sa_b / 8) : 0);
-    gp.sb = p->oz_scale_b + (b_batched ? buf * (sb_b / 8) : 0);
-    gp.a_batched = a_batched; gp.b_batched = b_batched;
-    gp.tiles_m = (int)((m + ec::oz::OM - 1) / ec::oz::OM);
-    gp.tiles_n = (int)((n + ec::oz::ON - 1) / ec::oz::ON);
-    gp.total_tiles = (int64_t)gp.tiles_m * gp.tiles_n * nb;
-    const int grid = (int)std::min<int64_t>(gp.total_tiles, p->sm_count - p->sm_margin);
-    kern<<<grid, ec::oz::OTHREADS, Cfg::SMEM_BYTES, main_stream>>>(tmA, tmB, gp);
-    EC_CUDA(cudaGetLastError());
-    p->launches++;
-    if (pipelined) EC_CUDA(cudaEventRecord(p->oz_ev_gemm[buf], main_stream));
-  }
-  p->last_kernel = "ozaki_i8_s7";
-  return EC_OK;
-}
-
-int dgemm_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n, int64_t k,
-                   double alpha, const double *A, int64_t lda, int64_t stride_a, const double *B,
-                   int64_t ldb, int64_t stride_b, double beta, double *C, int64_t ldc,
-                   int64_t stride_c, int64_t batch) {
-  if (!p) return fail(EC_ERR_ARG, "null pipeline");
-  if (m < 0 || n < 0 || k < 0 || batch < 0) return fail(EC_ERR_ARG, "negative dimension");
-  if ((transa != EC_OP_N && transa != EC_OP_T) || (transb != EC_OP_N && transb != EC_OP_T))
-    return fail(EC_ERR_ARG, "bad transpose flag");
-  if (m == 0 || n == 0 || batch == 0) return EC_OK;
-  const int64_t a_rows = transa ? k : m, b_rows = transb ? n : k;
-  if (lda < std::max<int64_t>(1, a_rows) || ldb < std::max<int64_t>(1, b_rows) ||
-      ldc < std::max<int64_t>(1, m))
-    return fail(EC_ERR_ARG, "leading dimension too small");
-  if (!C || (k > 0 && alpha != 0.0 && (!A || !B))) return fail(EC_ERR_ARG, "null operand");
-  DeviceGuard guard(p->device);
-
-  if (k == 0 || alpha == 0.0) {
-    const int64_t total = m * n * batch;
-    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)p->sm_count * 8);
-    ec::scale_kernel<<<grid, 256, 0, p->stream>>>(C, m, n, ldc, stride_c, batch, beta);
-    EC_CUDA(cudaGetLastError());
-    p->launches++;
-    p->last_kernel = "scale";
-    return EC_OK;
-  }
-
-  if (p->backend == EC_BACKEND_OZAKI_I8 && ozaki_eligible(m, n, k)) {
-    // k beyond what the int32 accumulators hold exactly: consecutive k-chunks, accumulated with beta = 1
-    for (int64_t k0 = 0; k0 < k; k0 += OZ_MAX_K) {
-      const int64_t kc = std::min(OZ_MAX_K, k - k0);
-      const double *Ak = A + (transa ? k0 : k0 * lda);
-      const double *Bk = B + (transb ? k0 * ldb : k0);
-      const int rc = ozaki_dispatch(p, transa, transb, m, n, kc, alpha, Ak, lda, stride_a, Bk, ldb, stride_b,
-                                    k0 == 0 ? beta : 1.0, C, ldc, stride_c, batch);
-      if (rc) return rc;
-    }
-    return EC_OK;
-  }
-
-  Operand oa{A, lda, stride_a, transa == EC_OP_T, m, k};
-  Operand ob{B, ldb, stride_b, transb == EC_OP_N, n, k};
-  // Tiny problems are latency-bound whichever kernel runs; the TMA pipeline only pays off once a
-  // problem has at least a small tile's worth of rows, columns and depth.
-  const bool big_enough = (m >= 32 && n >= 32 && k >= 16) && (m * n * k >= (int64_t)64 * 64 * 64);
-  const bool c_ok = m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31);
-  if (big_enough && c_ok && tma_ok(oa, batch) && tma_ok(ob, batch)) {
-    static const char *const nL[8] = {"tma_dmma_TN", "tma_dmma_TT", "tma_dmma_NN", "tma_dmma_NT",
-                                      "tma_dmma_TN_sk", "tma_dmma_TT_sk", "tma_dmma_NN_sk", "tma_dmma_NT_sk"};
-    static const char *const nS[8] = {"tma_dmma_TN_s", "tma_dmma_TT_s", "tma_dmma_NN_s", "tma_dmma_NT_s",
-                                      "tma_dmma_TN_s_sk", "tma_dmma_TT_s_sk", "tma_dmma_NN_s_sk", "tma_dmma_NT_s_sk"};
-    static const char *const nX[8] = {"tma_dmma_TN_xs", "tma_dmma_TT_xs", "tma_dmma_NN_xs", "tma_dmma_NT_xs",
-                                      "tma_dmma_TN_xs_sk", "tma_dmma_TT_xs_sk", "tma_dmma_NN_xs_sk", "tma_dmma_NT_xs_sk"};
-    const TileChoice ch = choose_tile(p, m, n, k, batch);
-    switch (ch.tile) {
-      case TILE_S: return run_tma_dmma<ec::CfgS>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nS);
-      case TILE_XS: return run_tma_dmma<ec::CfgXS>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nX);
-      default: return run_tma_dmma<ec::CfgL>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nL);
-    }
-  }
-
-  ec::SimtParams sp;
-  sp.M = m; sp.N = n; sp.K = k; sp.batch = batch;
-  sp.alpha = alpha; sp.beta = beta;
-  sp.A = A; sp.lda = lda; sp.stride_a = stride_a;
-  sp.B = B; sp.ldb = ldb; sp.stride_b = stride_b;
-  sp.C = C; sp.ldc = ldc; sp.stride_c = stride_c;
-  sp.transa = transa; sp.transb = transb;
-  sp.tiles_m = (int)((m + ec::SB - 1) / ec::SB);
-  sp.tiles_n = (int)((n + ec::SB - 1) / ec::SB);
-  sp.total_tiles = (int64_t)sp.tiles_m * sp.tiles_n * batch;
-  const int grid = (int)std::min<int64_t>(sp.total_tiles, (int64_t)p->sm_count * 4);
-  ec::dgemm_simt_kernel<<<grid, ec::SIMT_THREADS, 0, p->stream>>>(sp);
-  EC_CUDA(cudaGetLastError());
-  p->launches++;
-  p->last_kernel = "simt";
-  return EC_OK;
-}
-
-}  // namespace
-
-// ------------------------------------------------------------------------------------------
-// tensor-stream engine
-// ------------------------------------------------------------------------------------------
-// One job = the reference's whole streaming loop (README.md:62-66).  The tensor is cut into
-// chunks of `chunk` matrices; chunk c lives in ring slot c % ring.  Per slot: a device input
-// buffer, a device output buffer, (BASIS only) a device intermediate, and -- when the caller's
-// memory is pageable -- a pinned input and a pinned output staging buffer.  Three streams:
-//     h2d:     [wait compute(c-ring)]  copy chunk c in            -> ev_h2d[s]
-//     compute: [wait ev_h2d[s], d2h(c-ring)]  batched DGEMM(s)    -> ev_cmp[s]
-//     d2h:     [wait ev_cmp[s]]  copy chunk c out                 -> ev_d2h[s]
-// With pinned/registered caller memory the host thread only enqueues (DMA straight from/to the
-// caller's buffers).  With pageable memory a feeder thread stages chunks in (worker pool memcpy
-// into pinned) and a drainer thread stages results out, so both host copies overlap the GPU.
-struct StreamEngine {
-  ec_pipeline *p = nullptr;
-  cudaStream_t s_h2d = nullptr, s_cmp = nullptr, s_d2h = nullptr;
-  int ring = 0;
-  size_t in_bytes = 0, out_bytes = 0, tmp_bytes = 0, pin_in_bytes = 0, pin_out_bytes = 0;
-  std::vector<double *> d_in, d_out, d_tmp;
-  std::vector<void *> pin_in, pin_out;
-  std::vector<cudaEvent_t> ev_h2d, ev_cmp, ev_d2h;
-  double *d_fixed = nullptr;
-  size_t fixed_bytes = 0;
-  cudaEvent_t ev_fixed = nullptr;
-  CopyPool *pool_in = nullptr, *pool_out = nullptr;
-  int pool_threads = 0;
-
-  int ensure(int ring_, size_t in_b, size_t out_b, size_t tmp_b, size_t fixed_b, bool staged_in,
-             bool staged_out, int threads) {
-    if (!s_h2d) {
-      EC_CUDA(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
-      EC_CUDA(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
-      EC_CUDA(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
-      EC_CUDA(cudaEventCreateWithFlags(&ev_fixed, cudaEventDisableTiming));
-    }
-    if (ring_ != ring) {
-      int rc = release_buffers();
-      if (rc) return rc;
-      ring = ring_;
-      d_in.assign(ring, nullptr);
-      d_out.assign(ring, nullptr);
-      d_tmp.assign(ring, nullptr);
-      pin_in.assign(ring, nullptr);
-      pin_out.assign(ring, nullptr);
-      ev_h2d.assign(ring, nullptr);
-      ev_cmp.assign(ring, nullptr);
-      ev_d2h.assign(ring, nullptr);
-      for (int s = 0; s < ring; ++s) {
-        EC_CUDA(cudaEventCreateWithFlags(&ev_h2d[s], cudaEventDisableTiming));
-        EC_CUDA(cudaEventCreateWithFlags(&ev_cmp[s], cudaEventDisableTiming));
-        EC_CUDA(cudaEventCreateWithFlags(&ev_d2h[s], cudaEventDisableTiming));
-      }
-    }
-    auto grow_dev = [&](std::vector<double *> &v, size_t &have, size_t want) -> int {
-      if (want <= have) return EC_OK;
-      for (int s = 0; s < ring; ++s) {
-        if (v[s]) EC_CUDA(cudaFree(v[s]));
-        v[s] = nullptr;
-      }
-      have = 0;
-      for (int s = 0; s < ring; ++s) EC_CUDA(cudaMalloc((void **)&v[s], want));
-      have = want;
-      return EC_OK;
-    };
-    auto grow_pin = [&](std::vector<void *> &v, size_t &have, size_t want) -> int {
-      if (want <= have) return EC_OK;
-      for (int s = 0; s < ring; ++s) {
-        if (v[s]) EC_CUDA(cudaFreeHost(v[s]));
-        v[s] = nullptr;
-      }
-      have = 0;
-      for (int s = 0; s < ring; ++s) EC_CUDA(cudaHostAlloc(&v[s], want, cudaHostAllocDefault));
-      have = want;
-      return EC_OK;
-    };
-    int rc;
-    if ((rc = grow_dev(d_in, in_bytes, in_b))) return rc;
-    if ((rc = grow_dev(d_out, out_bytes, out_b))) return rc;
-    if (tmp_b && (rc = grow_dev(d_tmp, tmp_bytes, tmp_b))) return rc;
-    if (staged_in && (rc = grow_pin(pin_in, pin_in_bytes, in_b))) return rc;
-    if (staged_out && (rc = grow_pin(pin_out, pin_out_bytes, out_b))) return rc;
-    if (fixed_b > fixed_bytes) {
-      if (d_fixed) EC_CUDA(cudaFree(d_fixed));
-      d_fixed = nullptr;
-      fixed_bytes = 0;
-      EC_CUDA(cudaMalloc((void **)&d_fixed, fixed_b));
-      fixed_bytes = fixed_b;
-    }
-    if ((staged_in || staged_out) && (!pool_in || pool_threads != threads)) {
-      delete pool_in;
-      delete pool_out;
-      pool_in = new CopyPool(std::max(1, threads / 2));
-      pool_out = new CopyPool(std::max(1, threads - threads / 2));
-      pool_threads = threads;
-    }
-    return EC_OK;
-  }
-
-  int release_buffers() {
-    for (auto &x : d_in) if (x) { EC_CUDA(cudaFree(x)); x = nullptr; }
-    for (auto &x : d_out) if (x) { EC_CUDA(cudaFree(x)); x = nullptr; }
-    for (auto &x : d_tmp) if (x) { EC_CUDA(cudaFree(x)); x = nullptr; }
-    for (auto &x : pin_in) if (x) { EC_CUDA(cudaFreeHost(x)); x = nullptr; }
-    for (auto &x : pin_out) if (x) { EC_CUDA(cudaFreeHost(x)); x = nullptr; }
-    for (auto &e : ev_h2d) if (e) { cudaEventDestroy(e); e = nullptr; }
-    for (auto &e : ev_cmp) if (e) { cudaEventDestroy(e); e = nullptr; }
-    for (auto &e : ev_d2h) if (e) { cudaEventDestroy(e); e = nullptr; }
-    in_bytes = out_bytes = tmp_bytes = pin_in_bytes = pin_out_bytes = 0;
-    return EC_OK;
-  }
-
-  void destroy() {
-    release_buffers();
-    if (d_fixed) cudaFree(d_fixed);
-    d_fixed = nullptr;
-    if (ev_fixed) cudaEventDestroy(ev_fixed);
-    if (s_h2d) cudaStreamDestroy(s_h2d);
-    if (s_cmp) cudaStreamDestroy(s_cmp);
-    if (s_d2h) cudaStreamDestroy(s_d2h);
-    delete pool_in;
-    delete pool_out;
-    pool_in = pool_out = nullptr;
-  }
-};
-
-namespace {
-
-struct StreamShape {
-  int64_t r_rows, r_cols;  // result shape
-};
-
-int stream_shape(int kind, int64_t f_rows, int64_t f_cols, int64_t t_rows, int64_t t_cols,
-                 StreamShape *out) {
-  switch (kind) {
-    case EC_STREAM_RIGHT:  // T(t_rows x t_cols) * F(f_rows x f_cols)
-      if (t_cols != f_rows) return fail(EC_ERR_SHAPE, "Shape mismatch in gemm: T.cols != F.rows");
-      *out = {t_rows, f_cols};
-      return EC_OK;
-    case EC_STREAM_LEFT:
-      if (f_cols != t_rows) return fail(EC_ERR_SHAPE, "Shape mismatch in gemm: F.cols != T.rows");
-      *out = {f_rows, t_cols};
-      return EC_OK;
-    case EC_STREAM_LEFT_T:
-      if (f_rows != t_rows) return fail(EC_ERR_SHAPE, "Shape mismatch in gemm: F^T.cols != T.rows");
-      *out = {f_cols, t_cols};
-      return EC_OK;
-    case EC_STREAM_BASIS:
-      if (f_rows != t_rows || t_cols != f_rows)
-        return fail(EC_ERR_SHAPE, "Shape mismatch in basis transform F^T * T * F");
-      *out = {f_cols, f_cols};
-      return EC_OK;
-  }
-  return fail(EC_ERR_ARG, "unknown tensor-stream kind %d", kind);
-}
-
-// Launch the product(s) for `nb` matrices at d_in -> d_out on the pipeline's *current* stream.
-int stream_compute(ec_pipeline *p, int kind, const double *dF, int64_t f_rows, int64_t f_cols,
-                   const double *d_in, double *d_out, double *d_tmp, int64_t nb, int64_t t_rows,
-                   int64_t t_cols, const StreamShape &sh) {
-  const int64_t t_sz = t_rows * t_cols, r_sz = sh.r_rows * sh.r_cols;
-  switch (kind) {
-    case EC_STREAM_RIGHT:
-      return dgemm_dispatch(p, EC_OP_N, EC_OP_N, t_rows, f_cols, t_cols, 1.0, d_in, t_rows, t_sz,
-                            dF, f_rows, 0, 0.0, d_out, sh.r_rows, r_sz, nb);
-    case EC_STREAM_LEFT:
-      return dgemm_dispatch(p, EC_OP_N, EC_OP_N, f_rows, t_cols, f_cols, 1.0, dF, f_rows, 0, d_in,
-                            t_rows, t_sz, 0.0, d_out, sh.r_rows, r_sz, nb);
-    case EC_STREAM_LEFT_T:
-      return dgemm_dispatch(p, EC_OP_T, EC_OP_N, f_cols, t_cols, f_rows, 1.0, dF, f_rows, 0, d_in,
-                            t_rows, t_sz, 0.0, d_out, sh.r_rows, r_sz, nb);
-    case EC_STREAM_BASIS: {
-      const int64_t tmp_sz = f_cols * t_cols;
-      int rc = dgemm_dispatch(p, EC_OP_T, EC_OP_N, f_cols, t_cols, f_rows, 1.0, dF, f_rows, 0,
-                              d_in, t_rows, t_sz, 0.0, d_tmp, f_cols, tmp_sz, nb);
-      if (rc) return rc;
-      return dgemm_dispatch(p, EC_OP_N, EC_OP_N, f_cols, f_cols, t_cols, 1.0, d_tmp, f_cols,
-                            tmp_sz, dF, f_rows, 0, 0.0, d_out, sh.r_rows, r_sz, nb);
-    }
-  }
-  return fail(EC_ERR_ARG, "unknown tensor-stream kind %d", kind);
-}
-
-// Copy matrices [i0, i0+nb) between per-matrix host pointers and one contiguous device chunk,
-// merging runs of adjacent host matrices into single DMA transfers.
-int dma_chunk(bool to_device, double *dev, const double *const *host, int64_t i0, int64_t nb,
-              int64_t elems, cudaStream_t st) {
-  int64_t i = 0;
-  while (i < nb) {
-    int64_t j = i + 1;
-    while (j < nb && host[i0 + j] == host[i0 + j - 1] + elems) ++j;
-    const size_t bytes = (size_t)(j - i) * elems * 8;
-    if (to_device)
-      EC_CUDA(cudaMemcpyAsync(dev + i * elems, host[i0 + i], bytes, cudaMemcpyHostToDevice, st));
-    else
-      EC_CUDA(cudaMemcpyAsync((void *)host[i0 + i], dev + i * elems, bytes, cudaMemcpyDeviceToHost, st));
-    i = j;
-  }
-  return EC_OK;
-}
-
-}  // namespace
+// The host side is one translation unit, split by concern:
+#include "host_util.inl"        // errors, driver entry point, staging ring, copy pool
+#include "handles.inl"          // ec_pipeline / ec_matrix, stream registry, device guard
+#include "dgemm_launch.inl"     // native path: tensor maps, stream-K workspace, launch, cost model
+#include "ozaki_dispatch.inl"   // int8 emulation backend: split + GEMM launches
+#include "dgemm_dispatch.inl"   // validation, corner cases, backend / kernel choice
+#include "stream_engine.inl"    // overlapped tensor-stream engine
 
 // ------------------------------------------------------------------------------------------
 // C ABI

@@ -1,0 +1,80 @@
+// eigencuda_b200/csrc/handles.inl -- the opaque handles behind the C ABI (ec_pipeline, ec_matrix), stream registry, device guard
+// Part of the single translation unit ec_api.cu (included there, in order); not a standalone header.
+#pragma once
+
+// ------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------
+struct StreamEngine;
+
+struct ec_pipeline {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = true;
+  int backend = EC_BACKEND_FP64_DMMA;
+  int sm_count = 0;
+  int64_t launches = 0;
+  const char *last_kernel = "none";
+  StagingRing staging;
+  StreamEngine *engine = nullptr;
+  int cfg_chunk = 0, cfg_ring = 0, cfg_threads = 0;
+  // stream-K fix-up workspace (partial accumulator tiles + flags), allocated on first use
+  double *sk_workspace = nullptr;
+  unsigned *sk_flags = nullptr;
+  unsigned sk_epoch = 0;
+  int stream_k = 1;   // 0 disables the stream-K schedule (EC_STREAM_K=0)
+  int sm_margin = 0;  // SMs left free for concurrent kernels (NCCL during SUMMA)
+  int one_cta_per_tile = 0;  // non-persistent launch for long tiles (shared-GPU friendly)
+  // small direct-mapped cache of encoded tensor maps: the compat loop and every tensor-stream
+  // chunk reuse the same few device buffers, and cuTensorMapEncodeTiled costs about a microsecond
+  struct TmapEntry {
+    const void *ptr = nullptr;
+    int64_t inner = 0, outer = 0, batch = 0, ld = 0, stride = 0;
+    int box_outer = 0;
+    CUtensorMap map;
+  } tmap_cache[16];
+  // EC_BACKEND_OZAKI_I8 workspace: digit planes and row/column scales, grown on demand
+  int8_t *oz_planes_a = nullptr, *oz_planes_b = nullptr;
+  double *oz_scale_a = nullptr, *oz_scale_b = nullptr;
+  unsigned long long *oz_amax = nullptr;
+  size_t oz_planes_a_bytes = 0, oz_planes_b_bytes = 0, oz_scale_a_bytes = 0, oz_scale_b_bytes = 0, oz_amax_bytes = 0;
+  cudaStream_t oz_split_stream = nullptr;          // splits of chunk c+1 overlap the GEMM of chunk c
+  cudaEvent_t oz_ev_split[2] = {nullptr, nullptr}, oz_ev_gemm[2] = {nullptr, nullptr};
+};
+
+struct ec_matrix {
+  double *data = nullptr;
+  int64_t rows = 0, cols = 0;
+  cudaStream_t stream = nullptr;
+  int device = 0;
+};
+
+namespace {
+
+// stream -> pipeline registry, so that CudaMatrix (which only knows its stream, reference
+// include/cudamatrix.hpp:57) can find its pipeline's staging ring.
+std::mutex g_registry_mu;
+std::unordered_map<void *, ec_pipeline *> g_registry;
+
+ec_pipeline *pipeline_of_stream(cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_registry_mu);
+  auto it = g_registry.find((void *)s);
+  return it == g_registry.end() ? nullptr : it->second;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool active = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+      cudaSetDevice(dev);
+      active = true;
+    }
+  }
+  ~DeviceGuard() {
+    if (active) cudaSetDevice(prev);
+  }
+};
+
+
+}  // namespace
