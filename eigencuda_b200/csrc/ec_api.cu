@@ -535,13 +535,11 @@ int ec_tensor_stream_run(ec_pipeline *p, int kind, const double *F, int64_t f_ro
       EC_CUDA(cudaStreamWaitEvent(E.s_cmp, E.ev_h2d[s], 0));
       if (c >= ring) EC_CUDA(cudaStreamWaitEvent(E.s_cmp, E.ev_d2h[s], 0));  // d_out[s] drained
       {
-        cudaStream_t saved = p->stream;
-        p->stream = E.s_cmp;
+        StreamScope scope(p, E.s_cmp);
         rc = stream_compute(p, kind, dF, f_rows, f_cols, E.d_in[s], E.d_out[s],
                             kind == EC_STREAM_BASIS ? E.d_tmp[s] : nullptr, nb, t_rows, t_cols, sh);
-        p->stream = saved;
-        if (rc) return rc;
       }
+      if (rc) return rc;
       EC_CUDA(cudaEventRecord(E.ev_cmp[s], E.s_cmp));
       // D2H
       EC_CUDA(cudaStreamWaitEvent(E.s_d2h, E.ev_cmp[s], 0));

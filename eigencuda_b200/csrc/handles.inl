@@ -77,4 +77,15 @@ struct DeviceGuard {
 };
 
 
+// Run a few launches of this pipeline on another of its internal streams (the engine's compute
+// stream, the Ozaki split stream); restores the stream on every exit path.
+struct StreamScope {
+  ec_pipeline *p;
+  cudaStream_t saved;
+  StreamScope(ec_pipeline *p_, cudaStream_t s) : p(p_), saved(p_->stream) { p->stream = s; }
+  ~StreamScope() { p->stream = saved; }
+  StreamScope(const StreamScope &) = delete;
+  StreamScope &operator=(const StreamScope &) = delete;
+};
+
 }  // namespace

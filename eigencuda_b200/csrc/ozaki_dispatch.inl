@@ -118,10 +118,8 @@ int ozaki_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
   auto split_chunk = [&](int64_t c) -> int {
     const int64_t b0 = c * chunk, nb = std::min(chunk, batch - b0);
     const int buf = pipelined ? (int)(c & 1) : 0;
-    if (pipelined) {
-      p->stream = p->oz_split_stream;
-      if (c >= 2) EC_CUDA(cudaStreamWaitEvent(p->oz_split_stream, p->oz_ev_gemm[buf], 0));   // buffer consumed
-    }
+    StreamScope scope(p, pipelined ? p->oz_split_stream : main_stream);
+    if (pipelined && c >= 2) EC_CUDA(cudaStreamWaitEvent(p->oz_split_stream, p->oz_ev_gemm[buf], 0));   // buffer consumed
     int r = EC_OK;
     if (a_batched)
       r = oz_split(p, A + b0 * stride_a, a_rs, a_ks, stride_a, m, k, Kp, nb, p->oz_planes_a + buf * pa,
@@ -129,13 +127,7 @@ int ozaki_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
     if (!r && b_batched)
       r = oz_split(p, B + b0 * stride_b, b_rs, b_ks, stride_b, n, k, Kp, nb, p->oz_planes_b + buf * pb,
                    p->oz_scale_b + buf * (sb_b / 8), amax_buf[buf]);
-    if (pipelined) {
-      if (!r) {
-        cudaError_t e = cudaEventRecord(p->oz_ev_split[buf], p->oz_split_stream);
-        if (e != cudaSuccess) r = fail(EC_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
-      }
-      p->stream = main_stream;
-    }
+    if (!r && pipelined) EC_CUDA(cudaEventRecord(p->oz_ev_split[buf], p->oz_split_stream));
     return r;
   };
   if (pipelined) {
@@ -144,12 +136,12 @@ int ozaki_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
     EC_CUDA(cudaStreamWaitEvent(p->oz_split_stream, p->oz_ev_gemm[0], 0));
   }
   if (a_batched || b_batched) {
-    if ((rc = split_chunk(0))) { p->stream = main_stream; return rc; }
+    if ((rc = split_chunk(0))) return rc;
   }
   for (int64_t c = 0; c < nchunks; ++c) {
     const int64_t b0 = c * chunk, nb = std::min(chunk, batch - b0);
     const int buf = pipelined ? (int)(c & 1) : 0;
-    if (pipelined && c + 1 < nchunks && (rc = split_chunk(c + 1))) { p->stream = main_stream; return rc; }
+    if (pipelined && c + 1 < nchunks && (rc = split_chunk(c + 1))) return rc;
     if (!pipelined && c > 0 && (a_batched || b_batched) && (rc = split_chunk(c))) return rc;
     if (pipelined) EC_CUDA(cudaStreamWaitEvent(main_stream, p->oz_ev_split[buf], 0));
     CUtensorMap tmA, tmB;
