@@ -237,7 +237,7 @@ int ec_matrix_upload(ec_matrix *m, const double *host, int64_t count) {
     int slot = -1;
     int rc = p->staging.acquire(bytes, &slot);
     if (rc) return rc;
-    std::memcpy(p->staging.buf[slot], host, bytes);
+    staging_copy(p->staging.buf[slot], host, bytes);
     cudaError_t e =
         cudaMemcpyAsync(m->data, p->staging.buf[slot], bytes, cudaMemcpyHostToDevice, m->stream);
     if (e != cudaSuccess) return fail(EC_ERR_COPY, "Error copy arrays to device: %s", cudaGetErrorString(e));
@@ -292,7 +292,7 @@ int ec_matrix_download(const ec_matrix *m, double *host) {
       if (prev_slot >= 0) {
         EC_CUDA(cudaEventSynchronize(p->staging.ev[prev_slot]));
         p->staging.busy[prev_slot] = false;
-        std::memcpy((char *)host + prev_off, p->staging.buf[prev_slot], prev_len);
+        staging_copy((char *)host + prev_off, p->staging.buf[prev_slot], prev_len);
       }
       prev_slot = slot;
       prev_off = off;
@@ -496,7 +496,7 @@ int ec_tensor_stream_run(ec_pipeline *p, int kind, const double *F, int64_t f_ro
           E.pool_out->parallel_for(nb * pieces, [&](int64_t t) {
             const int64_t i = t / pieces, q = t % pieces;
             const size_t lo = (size_t)(r_sz * 8) * q / pieces, hi = (size_t)(r_sz * 8) * (q + 1) / pieces;
-            std::memcpy((char *)results[i0 + i] + lo, src + (size_t)i * r_sz * 8 + lo, hi - lo);
+            staging_copy((char *)results[i0 + i] + lo, src + (size_t)i * r_sz * 8 + lo, hi - lo);
           });
         }
         {
@@ -521,7 +521,7 @@ int ec_tensor_stream_run(ec_pipeline *p, int kind, const double *F, int64_t f_ro
         E.pool_in->parallel_for(nb * pieces, [&](int64_t t) {
           const int64_t i = t / pieces, q = t % pieces;
           const size_t lo = (size_t)(t_sz * 8) * q / pieces, hi = (size_t)(t_sz * 8) * (q + 1) / pieces;
-          std::memcpy(dst + (size_t)i * t_sz * 8 + lo, (const char *)tensor[i0 + i] + lo, hi - lo);
+          staging_copy(dst + (size_t)i * t_sz * 8 + lo, (const char *)tensor[i0 + i] + lo, hi - lo);
         });
       }
       if (c >= ring) EC_CUDA(cudaStreamWaitEvent(E.s_h2d, E.ev_cmp[s], 0));  // d_in[s] consumed

@@ -117,6 +117,46 @@ bool is_device_ptr(const void *p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Staging copy with streaming (non-temporal) stores.  Neither direction of the pageable <-> pinned
+// staging re-reads what it has just written, so ordinary stores only add a read-for-ownership of
+// every destination line: on this memcpy-bound path that is a third of the host memory traffic.
+// AVX2 when the CPU has it (checked once), std::memcpy otherwise and for small pieces.
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) inline void stream_copy_avx2(char *dst, const char *src, size_t n) {
+  // head: bring dst to 32-byte alignment
+  const size_t head = (32 - ((uintptr_t)dst & 31)) & 31;
+  if (head) {
+    std::memcpy(dst, src, head);
+    dst += head; src += head; n -= head;
+  }
+  size_t i = 0;
+  for (; i + 128 <= n; i += 128) {
+    const __m256i a = _mm256_loadu_si256((const __m256i *)(src + i));
+    const __m256i b = _mm256_loadu_si256((const __m256i *)(src + i + 32));
+    const __m256i c = _mm256_loadu_si256((const __m256i *)(src + i + 64));
+    const __m256i d = _mm256_loadu_si256((const __m256i *)(src + i + 96));
+    _mm256_stream_si256((__m256i *)(dst + i), a);
+    _mm256_stream_si256((__m256i *)(dst + i + 32), b);
+    _mm256_stream_si256((__m256i *)(dst + i + 64), c);
+    _mm256_stream_si256((__m256i *)(dst + i + 96), d);
+  }
+  _mm_sfence();
+  if (i < n) std::memcpy(dst + i, src + i, n - i);
+}
+#endif
+
+inline void staging_copy(void *dst, const void *src, size_t n) {
+#if defined(__x86_64__)
+  static const bool have_avx2 = __builtin_cpu_supports("avx2");
+  if (have_avx2 && n >= (size_t)64 << 10) {
+    stream_copy_avx2((char *)dst, (const char *)src, n);
+    return;
+  }
+#endif
+  std::memcpy(dst, src, n);
+}
+
 // Small persistent worker pool for pageable <-> pinned staging copies.
 class CopyPool {
  public:
