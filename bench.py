@@ -508,7 +508,24 @@ def main():
         extras["e2e_pageable"] = {"matrices": cp_, "n": n, "ms_per_step": 1e3 * dt, "matrices_per_s": cp_ / dt,
                                   "host_gbs_each_way": cp_ * elems * 8 / dt / 1e9,
                                   "host_memory": "pageable, staged through pinned ring by worker threads"}
-        del Tsrc, base, outs
+        # the reference's own loop shape through the compat API (copy_to_gpu -> gemm -> convert,
+        # pageable memory, one stream): what a caller gets with NO source change at all
+        cl = 256
+        ts_h = [np.asfortranarray(base[:, i].reshape(n, n, order="F")) for i in range(cl)]
+        cuma_A = ec.CudaMatrix(Fh, pipe.get_stream())
+        cuma_B = ec.CudaMatrix(n, n, pipe.get_stream())
+        cuma_C = ec.CudaMatrix(n, n, pipe.get_stream())
+        for t in ts_h[:8]:
+            cuma_B.copy_to_gpu(t); pipe.gemm(cuma_B, cuma_A, cuma_C); cuma_C.to_eigen()
+        t0 = time.perf_counter()
+        for t in ts_h:
+            cuma_B.copy_to_gpu(t)
+            pipe.gemm(cuma_B, cuma_A, cuma_C)
+            res_i = cuma_C.to_eigen()
+        dt = time.perf_counter() - t0
+        extras["compat_loop_pageable"] = {"matrices": cl, "n": n, "matrices_per_s": cl / dt,
+                                          "what": "README.md:62-66 loop through CudaMatrix/CudaPipeline of this repo, unchanged caller code"}
+        del Tsrc, base, outs, ts_h
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
