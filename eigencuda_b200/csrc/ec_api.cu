@@ -111,6 +111,8 @@ int ec_pipeline_destroy(ec_pipeline *p) {
     delete p->engine;
   }
   p->staging.destroy();
+  delete p->compat_pool;
+  p->compat_pool = nullptr;
   if (p->sk_workspace) cudaFree(p->sk_workspace);
   if (p->sk_flags) cudaFree(p->sk_flags);
   if (p->oz_planes_a) cudaFree(p->oz_planes_a);
@@ -223,6 +225,44 @@ int ec_matrix_free(ec_matrix *m) {
   return EC_OK;
 }
 
+namespace {
+// Pageable <-> pinned copy of one whole matrix for the reference's blocking calls
+// (src/cudamatrix.cc:8-12 and :47-51).  A single core moves about 12 GB/s, a quarter of what the
+// host link then takes it at, so anything of 1 MiB or more is cut into pieces for a few workers
+// plus the calling thread.
+void compat_copy(ec_pipeline *p, void *dst, const void *src, size_t bytes, bool prefault_only = false) {
+  constexpr size_t MIN_PARALLEL = (size_t)1 << 20, MIN_PIECE = (size_t)128 << 10;
+  auto piece_job = [&](void *d, const void *s, size_t n) {
+    if (prefault_only)
+      ec_host::prefault_for_write(d, n);
+    else
+      staging_copy(d, s, n);
+  };
+  if (bytes < MIN_PARALLEL) {
+    piece_job(dst, src, bytes);
+    return;
+  }
+  if (!p->compat_pool_tried) {
+    p->compat_pool_tried = true;
+    int workers = std::max(1, std::min(5, (int)std::thread::hardware_concurrency() / 3));
+    if (const char *e = std::getenv("EC_COMPAT_THREADS")) workers = std::max(0, std::atoi(e) - 1);
+    if (workers > 0) p->compat_pool = new CopyPool(workers);
+  }
+  if (!p->compat_pool) {
+    piece_job(dst, src, bytes);
+    return;
+  }
+  const size_t lanes = (size_t)p->compat_pool->size() + 1;
+  size_t piece = std::max(MIN_PIECE, (bytes + lanes - 1) / lanes);
+  piece = (piece + 4095) & ~(size_t)4095;
+  const int64_t pieces = (int64_t)((bytes + piece - 1) / piece);
+  p->compat_pool->parallel_for(pieces, [&](int64_t i) {
+    const size_t lo = (size_t)i * piece, hi = std::min(bytes, lo + piece);
+    piece_job((char *)dst + lo, (const char *)src + lo, hi - lo);
+  });
+}
+}  // namespace
+
 int ec_matrix_upload(ec_matrix *m, const double *host, int64_t count) {
   if (!m) return fail(EC_ERR_ARG, "null matrix");
   if (count < 0 || count > m->rows * m->cols)
@@ -237,7 +277,7 @@ int ec_matrix_upload(ec_matrix *m, const double *host, int64_t count) {
     int slot = -1;
     int rc = p->staging.acquire(bytes, &slot);
     if (rc) return rc;
-    staging_copy(p->staging.buf[slot], host, bytes);
+    compat_copy(p, p->staging.buf[slot], host, bytes);
     cudaError_t e =
         cudaMemcpyAsync(m->data, p->staging.buf[slot], bytes, cudaMemcpyHostToDevice, m->stream);
     if (e != cudaSuccess) return fail(EC_ERR_COPY, "Error copy arrays to device: %s", cudaGetErrorString(e));
@@ -271,9 +311,10 @@ int ec_matrix_download(const ec_matrix *m, double *host) {
   DeviceGuard guard(m->device);
   const size_t bytes = (size_t)count * sizeof(double);
   ec_pipeline *p = pipeline_of_stream(m->stream);
-  constexpr size_t CHUNK = (size_t)4 << 20;
-  if (p && bytes > CHUNK && !is_pinned_host(host)) {
-    // Pageable destination: DMA into two pinned slots alternately and copy out behind the DMA.
+  // Pageable destination of 1 MiB or more: DMA into two pinned slots alternately and copy out
+  // behind the DMA, in 4 MiB pieces (two halves for anything smaller than 8 MiB).
+  const size_t CHUNK = std::min((size_t)4 << 20, (bytes / 2 + 4095) & ~(size_t)4095);
+  if (p && bytes >= ((size_t)1 << 20) && !is_pinned_host(host)) {
     size_t off = 0;
     int prev_slot = -1;
     size_t prev_off = 0, prev_len = 0;
@@ -288,11 +329,12 @@ int ec_matrix_download(const ec_matrix *m, double *host) {
                                 cudaMemcpyDeviceToHost, m->stream));
         rc = p->staging.release_after(slot, m->stream);
         if (rc) return rc;
+        if (off == 0) compat_copy(p, host, host, bytes, /*prefault_only=*/true);   // behind the first DMA
       }
       if (prev_slot >= 0) {
         EC_CUDA(cudaEventSynchronize(p->staging.ev[prev_slot]));
         p->staging.busy[prev_slot] = false;
-        staging_copy((char *)host + prev_off, p->staging.buf[prev_slot], prev_len);
+        compat_copy(p, (char *)host + prev_off, p->staging.buf[prev_slot], prev_len);
       }
       prev_slot = slot;
       prev_off = off;

@@ -17,6 +17,10 @@ struct ec_pipeline {
   const char *last_kernel = "none";
   StagingRing staging;
   StreamEngine *engine = nullptr;
+  // workers for the matrix-at-a-time staging copies of copy_to_gpu / the conversion back
+  // (created on the first pageable transfer of 1 MiB or more; EC_COMPAT_THREADS=0 disables)
+  CopyPool *compat_pool = nullptr;
+  bool compat_pool_tried = false;
   int cfg_chunk = 0, cfg_ring = 0, cfg_threads = 0;
   // stream-K fix-up workspace (partial accumulator tiles + flags), allocated on first use
   double *sk_workspace = nullptr;

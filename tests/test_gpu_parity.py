@@ -350,7 +350,8 @@ def test_strided_batched_matches_loop(pipe, ta, tb):
 # ---------------------------------------------------------------------------------------------
 # memory subsystem: round trips are bit-exact, including the staged large-transfer paths
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(1, 1), (3, 2), (1000, 1000), (1537, 911)])
+@pytest.mark.parametrize("shape", [(1, 1), (3, 2), (256, 255), (512, 512), (1031, 257), (517, 1100),
+                                   (1000, 1000), (1537, 911)])
 def test_upload_download_bit_exact(pipe, shape):
     A = rnd(shape[0], shape)
     dA = ec.CudaMatrix(A, pipe.get_stream())

@@ -154,3 +154,19 @@ def test_summa_layout_covers_everything():
                 q, lo = L.a_owner_col(k0); assert lo <= k0 and k1 <= summa.block_range(k, L.Q, q)[1]
                 p, lo = L.b_owner_row(k0); assert lo <= k0 and k1 <= summa.block_range(k, L.P, p)[1]
         assert (seenC == 1).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side copy pool (csrc/copy_pool.hpp): plain C++, stress-tested on the CPU
+# ---------------------------------------------------------------------------------------------
+def test_copy_pool_stress(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_copy_pool")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", os.path.join(root, "tests", "cpp", "test_copy_pool.cc"),
+                    "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0 and "ALL PASSED" in out.stdout, out.stdout + out.stderr
