@@ -82,6 +82,12 @@ inline void prefault_for_write(void *p, size_t n) {
 #ifndef MADV_POPULATE_WRITE
 #define MADV_POPULATE_WRITE 23
 #endif
+  // Recycled heap memory is already mapped and walking its page tables would cost a third of the
+  // copy: look at the first and the last page and leave if both are resident.
+  unsigned char first = 0, last = 0;
+  if (mincore((void *)lo, 4096, &first) == 0 && mincore((void *)(hi - 4096), 4096, &last) == 0 &&
+      (first & 1) && (last & 1))
+    return;
   if (madvise((void *)lo, hi - lo, MADV_POPULATE_WRITE) != 0 && errno == EINVAL)
     usable.store(0, std::memory_order_relaxed);
 #else

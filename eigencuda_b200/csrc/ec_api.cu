@@ -538,6 +538,8 @@ int ec_tensor_stream_run(ec_pipeline *p, int kind, const double *F, int64_t f_ro
           E.pool_out->parallel_for(nb * pieces, [&](int64_t t) {
             const int64_t i = t / pieces, q = t % pieces;
             const size_t lo = (size_t)(r_sz * 8) * q / pieces, hi = (size_t)(r_sz * 8) * (q + 1) / pieces;
+            // result matrices are often freshly allocated: map the piece in one call, not per page
+            ec_host::prefault_for_write((char *)results[i0 + i] + lo, hi - lo);
             staging_copy((char *)results[i0 + i] + lo, src + (size_t)i * r_sz * 8 + lo, hi - lo);
           });
         }
