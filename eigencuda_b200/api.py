@@ -279,3 +279,27 @@ class PinnedBuffer:
             self.close()
         except Exception:
             pass
+
+
+class host_pin:
+    """Pins numpy arrays the caller already owns, in place, while the context is open
+    (ec_host_register): transfers from / to them are plain DMA and
+    skip the staging copy.  The arrays must stay alive and must not be reallocated meanwhile."""
+
+    def __init__(self, *arrays):
+        self._arrays = [a for a in arrays if a.size]
+        self._done = []
+
+    def __enter__(self):
+        for a in self._arrays:
+            if not (a.flags.f_contiguous or a.flags.c_contiguous):
+                raise ValueError("host_pin needs contiguous arrays")
+            check(lib.ec_host_register(C.c_void_p(a.ctypes.data), a.nbytes))
+            self._done.append(a)
+        return self
+
+    def __exit__(self, *exc):
+        for a in self._done:
+            lib.ec_host_unregister(C.c_void_p(a.ctypes.data))
+        self._done = []
+        return False

@@ -19,6 +19,7 @@ int dgemm_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
     return fail(EC_ERR_ARG, "leading dimension too small");
   if (!C || (k > 0 && alpha != 0.0 && (!A || !B))) return fail(EC_ERR_ARG, "null operand");
   DeviceGuard guard(p->device);
+  TraceRange trace("ec_dgemm");
 
   if (k == 0 || alpha == 0.0) {
     const int64_t total = m * n * batch;

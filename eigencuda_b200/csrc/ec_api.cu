@@ -7,6 +7,7 @@
 // launch of a kernel from dgemm_kernels.cuh.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <atomic>
@@ -271,6 +272,7 @@ int ec_matrix_upload(ec_matrix *m, const double *host, int64_t count) {
   if (count == 0) return EC_OK;
   if (!host) return fail(EC_ERR_ARG, "null host pointer");
   DeviceGuard guard(m->device);
+  TraceRange trace("ec_matrix_upload");
   const size_t bytes = (size_t)count * sizeof(double);
   ec_pipeline *p = pipeline_of_stream(m->stream);
   if (p && !is_pinned_host(host)) {
@@ -309,6 +311,7 @@ int ec_matrix_download(const ec_matrix *m, double *host) {
   if (count == 0) return EC_OK;
   if (!host) return fail(EC_ERR_ARG, "null host pointer");
   DeviceGuard guard(m->device);
+  TraceRange trace("ec_matrix_download");
   const size_t bytes = (size_t)count * sizeof(double);
   ec_pipeline *p = pipeline_of_stream(m->stream);
   // Pageable destination of 1 MiB or more: DMA into two pinned slots alternately and copy out
@@ -448,6 +451,7 @@ int ec_tensor_stream_run(ec_pipeline *p, int kind, const double *F, int64_t f_ro
     return EC_OK;
   }
   DeviceGuard guard(p->device);
+  TraceRange trace("ec_tensor_stream_run");
 
   // ---- plan ----
   bool in_pinned = true, out_pinned = true;
@@ -532,6 +536,7 @@ int ec_tensor_stream_run(ec_pipeline *p, int kind, const double *F, int64_t f_ro
           drain_rc = EC_ERR_CUDA;
         } else {
           const int64_t i0 = c * chunk, nb = std::min(chunk, count - i0);
+          TraceRange trace_chunk("deliver chunk (pinned -> caller)");
           const char *src = (const char *)E.pin_out[s];
           // split every matrix into a few pieces so the pool stays busy even for small chunks
           const int pieces = std::max<int>(1, (int)std::min<int64_t>(8, (r_sz * 8) >> 18));
@@ -560,6 +565,7 @@ int ec_tensor_stream_run(ec_pipeline *p, int kind, const double *F, int64_t f_ro
       // H2D
       if (staged_in) {
         if (c >= ring) EC_CUDA(cudaEventSynchronize(E.ev_h2d[s]));  // pinned_in[s] consumed
+        TraceRange trace_chunk("stage chunk (caller -> pinned)");
         char *dst = (char *)E.pin_in[s];
         const int pieces = std::max<int>(1, (int)std::min<int64_t>(8, (t_sz * 8) >> 18));
         E.pool_in->parallel_for(nb * pieces, [&](int64_t t) {
@@ -643,6 +649,30 @@ int ec_host_alloc(size_t bytes, void **out) {
 }
 int ec_host_free(void *ptr) {
   if (ptr) EC_CUDA(cudaFreeHost(ptr));
+  return EC_OK;
+}
+
+int ec_host_register(void *ptr, size_t bytes) {
+  if (bytes == 0) return EC_OK;
+  if (!ptr) return fail(EC_ERR_ARG, "null host pointer");
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return EC_OK;
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(EC_ERR_NOMEM, "cudaHostRegister of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+  }
+  return EC_OK;
+}
+int ec_host_unregister(void *ptr) {
+  if (!ptr) return EC_OK;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(EC_ERR_ARG, "cudaHostUnregister failed: %s", cudaGetErrorString(e));
+  }
   return EC_OK;
 }
 

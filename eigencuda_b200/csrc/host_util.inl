@@ -31,6 +31,17 @@ int fail(int code, const char *fmt, ...) {
   } while (0)
 
 // ------------------------------------------------------------------------------------------
+// NVTX ranges: the library's phases show up by name on a profiler
+// timeline.  nvtx3 is header-only and costs one pointer test per call when no tool is attached.
+// ------------------------------------------------------------------------------------------
+struct TraceRange {
+  explicit TraceRange(const char *name) { nvtxRangePushA(name); }
+  ~TraceRange() { nvtxRangePop(); }
+  TraceRange(const TraceRange &) = delete;
+  TraceRange &operator=(const TraceRange &) = delete;
+};
+
+// ------------------------------------------------------------------------------------------
 // driver entry point for tensor-map encoding (no link-time dependency on libcuda, so the
 // library loads -- and its symbols can be checked -- on a machine without a GPU driver)
 // ------------------------------------------------------------------------------------------

@@ -13,6 +13,8 @@
 
 #include <memory>
 #include <stdexcept>
+#include <utility>
+#include <vector>
 #include <string>
 
 #include "eigencuda_b200.h"
@@ -35,6 +37,35 @@ inline void throw_on_error(int rc) {
   if (rc != EC_OK) throw std::runtime_error(ec_last_error_string());
 }
 }  // namespace detail
+
+// Additive: pins the storage of host matrices the caller already owns, in place, for as long as
+// this object lives.  Transfers from / to pinned memory are plain
+// DMA: copy_to_gpu, the conversion back and the tensor-level calls skip their staging copies.
+// Worth it for matrices that are transferred more than once; the matrices must not be resized or
+// destroyed while pinned.
+class HostPin {
+ public:
+  HostPin() = default;
+  explicit HostPin(const Eigen::MatrixXd &m) { add(m); }
+  explicit HostPin(const std::vector<Eigen::MatrixXd> &tensor) {
+    for (const Eigen::MatrixXd &m : tensor) add(m);
+  }
+  void add(const Eigen::MatrixXd &m) {
+    if (m.size() == 0) return;
+    void *ptr = const_cast<double *>(m.data());
+    detail::throw_on_error(ec_host_register(ptr, static_cast<size_t>(m.size()) * sizeof(double)));
+    _ranges.push_back(ptr);
+  }
+  ~HostPin() {
+    for (void *ptr : _ranges) ec_host_unregister(ptr);
+  }
+  HostPin(const HostPin &) = delete;
+  HostPin &operator=(const HostPin &) = delete;
+  HostPin(HostPin &&other) noexcept : _ranges(std::move(other._ranges)) { other._ranges.clear(); }
+
+ private:
+  std::vector<void *> _ranges;
+};
 
 class CudaPipeline;
 

@@ -167,6 +167,13 @@ int ec_pipeline_set_stream_config(ec_pipeline *p, int chunk_matrices, int ring_d
 /* Pinned host allocation (what CHANGELOG.md:32 records the reference once defaulted to). */
 int ec_host_alloc(size_t bytes, void **out);
 int ec_host_free(void *ptr);
+/* Pin memory the caller already owns -- the storage of an Eigen::MatrixXd, a std::vector<double>
+ * -- in place, so that copy_to_gpu, the conversion back and ec_tensor_stream_run move it by DMA
+ * without a staging copy.  The range must stay allocated until
+ * ec_host_unregister.  Registering costs about a millisecond per 16 MiB: worth it for buffers
+ * that are reused, not for one transfer.  Zero bytes or an already-pinned range is EC_OK. */
+int ec_host_register(void *ptr, size_t bytes);
+int ec_host_unregister(void *ptr);
 /* x = 2u-1, u in [0,1): splitmix64 on (seed, matrix_id, column-major index); bit-identical to
  * oracle_fill_uniform.  Fills `count` doubles at device pointer dst. */
 int ec_fill_uniform(ec_pipeline *p, uint64_t seed, uint64_t matrix_id, double *dst, int64_t count);

@@ -109,6 +109,11 @@ static void additive_api() {
     EXPECT(left_t[i].isApprox(fixed_t * tensor[i]));
     EXPECT(basis[i].isApprox((fixed_t * tensor[i]) * fixed));
   }
+  {
+    ecu::HostPin pin_tensor(tensor), pin_fixed(fixed);   // caller memory pinned in place: same results
+    std::vector<Mat> right_pinned = pipeline.right_multiply(tensor, fixed);
+    for (ecu::Index i = 0; i < count; ++i) EXPECT(right_pinned[i].isApprox(right[i]));
+  }
   ecu::CudaMatrix d_a{fixed, pipeline.get_stream()}, d_b{tensor[0], pipeline.get_stream()};
   ecu::CudaMatrix d_c{n, n, pipeline.get_stream()};
   pipeline.gemm(true, true, 1.0, d_a, d_b, 0.0, d_c);

@@ -437,6 +437,31 @@ def test_tensor_stream_kinds(pipe, kind, pinned):
         b.close()
 
 
+def test_host_pin_registers_caller_memory_in_place(pipe):
+    """ec_host_register: matrices the caller already owns, pinned in place, go
+    through the direct-DMA paths of copy_to_gpu / conversion / tensor stream; results identical."""
+    n, count = 192, 9
+    F = orc.fill_uniform(orc.SEED, 0, (n, n))
+    ts = [orc.fill_uniform(orc.SEED, i + 1, (n, n)) for i in range(count)]
+    outs = [np.empty((n, n), order="F") for _ in range(count)]
+    want = orc.tensor_stream("right", F, ts, flavour="fast")
+    with ec.host_pin(F, *ts, *outs):
+        with ec.host_pin(ts[0]):          # registering twice is not an error
+            pass
+        res = pipe.tensor_stream(ec.EC_STREAM_RIGHT, F, ts, results=outs)
+        for r, w in zip(res, want):
+            assert orc.rel_frobenius(r, w) <= TOL
+        big = orc.fill_uniform(7, 3, (700, 600))      # 3.4 MB: the chunked download path if pageable
+        with ec.host_pin(big):
+            d = ec.CudaMatrix(big, pipe.get_stream())
+            pipe.synchronize()                        # a pinned source is read asynchronously
+            assert np.array_equal(d.to_eigen(), big)
+    # unpinned again: the staged paths give the same bytes
+    res2 = pipe.tensor_stream(ec.EC_STREAM_RIGHT, F, ts)
+    for r, r2 in zip(outs, res2):
+        assert np.array_equal(r, r2)
+
+
 def test_tensor_stream_mixed_host_memory_and_device_fixed(pipe):
     """Pinned inputs with pageable outputs (and the reverse), and a fixed operand that already
     lives on the device (what the multi-GPU broadcast leaves behind): detected per buffer."""
