@@ -57,16 +57,30 @@ class CudaPipeline {
                                               const Eigen::MatrixXd &A) const {
     return stream(EC_STREAM_RIGHT, A, tensor);
   }
+  // same, into result matrices the caller keeps (reused in place when they have the right shape)
+  void right_multiply(const std::vector<Eigen::MatrixXd> &tensor, const Eigen::MatrixXd &A,
+                      std::vector<Eigen::MatrixXd> &results) const {
+    stream_into(EC_STREAM_RIGHT, A, tensor, results);
+  }
   // results[i] = A * tensor[i]   (transposeA: A^T * tensor[i])
   std::vector<Eigen::MatrixXd> left_multiply(const Eigen::MatrixXd &A,
                                              const std::vector<Eigen::MatrixXd> &tensor,
                                              bool transposeA = false) const {
     return stream(transposeA ? EC_STREAM_LEFT_T : EC_STREAM_LEFT, A, tensor);
   }
+  void left_multiply(const Eigen::MatrixXd &A, const std::vector<Eigen::MatrixXd> &tensor,
+                     std::vector<Eigen::MatrixXd> &results, bool transposeA = false) const {
+    stream_into(transposeA ? EC_STREAM_LEFT_T : EC_STREAM_LEFT, A, tensor, results);
+  }
   // results[i] = A^T * tensor[i] * A
   std::vector<Eigen::MatrixXd> basis_transform(const Eigen::MatrixXd &A,
                                                const std::vector<Eigen::MatrixXd> &tensor) const {
     return stream(EC_STREAM_BASIS, A, tensor);
+  }
+
+  void basis_transform(const Eigen::MatrixXd &A, const std::vector<Eigen::MatrixXd> &tensor,
+                       std::vector<Eigen::MatrixXd> &results) const {
+    stream_into(EC_STREAM_BASIS, A, tensor, results);
   }
 
   ec_pipeline *handle() const { return _p; }
@@ -75,7 +89,17 @@ class CudaPipeline {
   std::vector<Eigen::MatrixXd> stream(int kind, const Eigen::MatrixXd &A,
                                       const std::vector<Eigen::MatrixXd> &tensor) const {
     std::vector<Eigen::MatrixXd> results;
-    if (tensor.empty()) return results;
+    stream_into(kind, A, tensor, results);
+    return results;
+  }
+
+  // Elements of `results` that already have the result shape are written in place (so a caller
+  // that keeps -- and perhaps pins -- its result matrices across calls pays no allocation); the
+  // vector is resized and the other elements are reallocated.
+  void stream_into(int kind, const Eigen::MatrixXd &A, const std::vector<Eigen::MatrixXd> &tensor,
+                   std::vector<Eigen::MatrixXd> &results) const {
+    results.resize(tensor.size());
+    if (tensor.empty()) return;
     const Index tr = tensor[0].rows(), tc = tensor[0].cols();
     Index rr = 0, rc = 0;
     switch (kind) {
@@ -86,18 +110,16 @@ class CudaPipeline {
     }
     std::vector<const double *> in(tensor.size());
     std::vector<double *> out(tensor.size());
-    results.reserve(tensor.size());
     for (size_t i = 0; i < tensor.size(); ++i) {
       if (tensor[i].rows() != tr || tensor[i].cols() != tc)
         throw std::runtime_error("Shape mismatch in Cublas gemm");
-      results.emplace_back(rr, rc);
+      if (results[i].rows() != rr || results[i].cols() != rc) results[i] = Eigen::MatrixXd(rr, rc);
       in[i] = tensor[i].data();
       out[i] = results[i].data();
     }
     detail::throw_on_error(ec_tensor_stream_run(_p, kind, A.data(), A.rows(), A.cols(), in.data(),
                                                 out.data(), static_cast<int64_t>(tensor.size()),
                                                 tr, tc));
-    return results;
   }
 
   ec_pipeline *_p = nullptr;

@@ -113,6 +113,15 @@ static void additive_api() {
     ecu::HostPin pin_tensor(tensor), pin_fixed(fixed);   // caller memory pinned in place: same results
     std::vector<Mat> right_pinned = pipeline.right_multiply(tensor, fixed);
     for (ecu::Index i = 0; i < count; ++i) EXPECT(right_pinned[i].isApprox(right[i]));
+    // results the caller keeps (and pins) across calls are written in place
+    std::vector<Mat> kept(count, Mat::Zero(n, n));
+    const double *storage = kept[3].data();
+    ecu::HostPin pin_results(kept);
+    pipeline.left_multiply(fixed, tensor, kept, true);
+    EXPECT(kept[3].data() == storage);
+    for (ecu::Index i = 0; i < count; ++i) EXPECT(kept[i].isApprox(left_t[i]));
+    pipeline.basis_transform(fixed, tensor, kept);
+    for (ecu::Index i = 0; i < count; ++i) EXPECT(kept[i].isApprox(basis[i]));
   }
   ecu::CudaMatrix d_a{fixed, pipeline.get_stream()}, d_b{tensor[0], pipeline.get_stream()};
   ecu::CudaMatrix d_c{n, n, pipeline.get_stream()};
