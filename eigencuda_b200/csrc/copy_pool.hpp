@@ -104,7 +104,10 @@ inline void prefault_for_write(void *p, size_t n) {
 // costs about as much as the copy.
 class CopyPool {
  public:
-  explicit CopyPool(int n) {
+  // spin_us: how long an idle worker keeps polling before it sleeps.  Should cover the gap between
+  // two jobs of a steady caller: once workers start sleeping every job pays a wake-up, the caller's
+  // loop gets slower, and the gaps stay long (measured as two stable speeds a factor 1.8 apart).
+  explicit CopyPool(int n, int spin_us = 150) : spin_us_(spin_us) {
     for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
   }
   ~CopyPool() {
@@ -163,7 +166,7 @@ class CopyPool {
   void run() {
     uint64_t seen = 0;   // generation of the last job this worker looked at
     for (;;) {
-      // poll for ~150 us, then sleep until the generation moves
+      // poll for spin_us_, then sleep until the generation moves
       bool fresh = false;
       const auto t0 = std::chrono::steady_clock::now();
       for (int spin = 0;; ++spin) {
@@ -174,7 +177,7 @@ class CopyPool {
         }
         cpu_relax();
         if ((spin & 255) == 255 &&
-            std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(150))
+            std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us_))
           break;
       }
       if (!fresh) {
@@ -190,6 +193,7 @@ class CopyPool {
       drain();
     }
   }
+  const int spin_us_;
   std::vector<std::thread> workers_;
   std::mutex mu_;
   std::condition_variable cv_;

@@ -83,6 +83,28 @@ static int pipeline_create_impl(int device, cudaStream_t external, bool use_exte
       return fail(EC_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
     }
   }
+  // Device buffers of CudaMatrix come from the device's stream-ordered memory pool: constructing
+  // and destroying matrices inside a loop (the reference pays cudaMemGetInfo + cudaMalloc and a
+  // device-synchronising cudaFree each time, src/cudamatrix.cc:53-79) then costs microseconds and
+  // does not stall the stream.  Freed blocks stay cached up to 1 GiB.  EC_MEM_POOL=0 turns it off.
+  {
+    int supported = 0;
+    const char *env = std::getenv("EC_MEM_POOL");
+    if (!(env && env[0] == '0') &&
+        cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev) == cudaSuccess && supported) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t have = 0;
+        const uint64_t want = (uint64_t)1 << 30;
+        if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &have) == cudaSuccess && have < want) {
+          uint64_t v = want;
+          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &v);
+        }
+        p->mem_pool = true;
+      }
+    }
+    cudaGetLastError();
+  }
   {
     std::lock_guard<std::mutex> lk(g_registry_mu);
     g_registry[(void *)p->stream] = p;
@@ -194,8 +216,9 @@ int ec_matrix_alloc(void *cuda_stream, int64_t rows, int64_t cols, ec_matrix **o
   // not fit (src/cudamatrix.cc:63-79).  Same observable behaviour, but the query (a device
   // synchronising call) is only made when cudaMalloc has actually failed.
   double *d = nullptr;
+  const bool pooled = p && p->mem_pool;
   if (bytes > 0) {
-    cudaError_t e = cudaMalloc((void **)&d, bytes);
+    cudaError_t e = pooled ? cudaMallocAsync((void **)&d, bytes, st) : cudaMalloc((void **)&d, bytes);
     if (e != cudaSuccess) {
       cudaGetLastError();
       size_t free_b = 0, total_b = 0;
@@ -212,6 +235,7 @@ int ec_matrix_alloc(void *cuda_stream, int64_t rows, int64_t cols, ec_matrix **o
   m->cols = cols;
   m->stream = st;
   m->device = dev;
+  m->pooled = pooled && d != nullptr;
   *out = m;
   return EC_OK;
 }
@@ -220,7 +244,15 @@ int ec_matrix_free(ec_matrix *m) {
   if (!m) return EC_OK;
   if (m->data) {
     DeviceGuard guard(m->device);
-    cudaFree(m->data);  // synchronises with outstanding work on the buffer
+    // Pooled buffers are released in stream order, behind the work that still uses them.  If the
+    // matrix has outlived its pipeline (the reference tolerates that: its deleter is a plain
+    // cudaFree, include/cudamatrix.hpp:46) the stream may be gone, and cudaFree -- legal for pool
+    // memory, and synchronising -- is used instead.
+    ec_pipeline *p = m->pooled ? pipeline_of_stream(m->stream) : nullptr;
+    if (!(p && p->device == m->device && cudaFreeAsync(m->data, m->stream) == cudaSuccess)) {
+      cudaGetLastError();
+      cudaFree(m->data);  // synchronises with outstanding work on the buffer
+    }
   }
   delete m;
   return EC_OK;
@@ -232,7 +264,7 @@ namespace {
 // host link then takes it at, so anything of 1 MiB or more is cut into pieces for a few workers
 // plus the calling thread.
 void compat_copy(ec_pipeline *p, void *dst, const void *src, size_t bytes, bool prefault_only = false) {
-  constexpr size_t MIN_PARALLEL = (size_t)1 << 20, MIN_PIECE = (size_t)128 << 10;
+  constexpr size_t MIN_PARALLEL = (size_t)1 << 20, MIN_PIECE = (size_t)64 << 10;
   auto piece_job = [&](void *d, const void *s, size_t n) {
     if (prefault_only)
       ec_host::prefault_for_write(d, n);
@@ -247,14 +279,17 @@ void compat_copy(ec_pipeline *p, void *dst, const void *src, size_t bytes, bool 
     p->compat_pool_tried = true;
     int workers = std::max(1, std::min(5, (int)std::thread::hardware_concurrency() / 3));
     if (const char *e = std::getenv("EC_COMPAT_THREADS")) workers = std::max(0, std::atoi(e) - 1);
-    if (workers > 0) p->compat_pool = new CopyPool(workers);
+    // 1 ms of polling covers a whole iteration of the reference's loop at 512^2 .. 1000^2
+    if (workers > 0) p->compat_pool = new CopyPool(workers, 1000);
   }
   if (!p->compat_pool) {
     piece_job(dst, src, bytes);
     return;
   }
+  // four pieces per thread, handed out dynamically: a worker that shares its core with somebody
+  // else (SMT sibling, a busy neighbour VM) then simply takes fewer of them
   const size_t lanes = (size_t)p->compat_pool->size() + 1;
-  size_t piece = std::max(MIN_PIECE, (bytes + lanes - 1) / lanes);
+  size_t piece = std::max(MIN_PIECE, (bytes + 4 * lanes - 1) / (4 * lanes));
   piece = (piece + 4095) & ~(size_t)4095;
   const int64_t pieces = (int64_t)((bytes + piece - 1) / piece);
   p->compat_pool->parallel_for(pieces, [&](int64_t i) {
@@ -376,13 +411,18 @@ int ec_gemm(ec_pipeline *p, const ec_matrix *A, const ec_matrix *B, ec_matrix *C
   int rc = dgemm_dispatch(p, EC_OP_N, EC_OP_N, A->rows, B->cols, A->cols, 1.0, A->data, A->rows, 0,
                           B->data, B->rows, 0, 0.0, C->data, std::max<int64_t>(C->rows, 1), 0, 1);
   if (rc) return rc;
-  if (C->stream != p->stream) {
-    cudaEvent_t ev;
-    EC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    EC_CUDA(cudaEventRecord(ev, p->stream));
-    EC_CUDA(cudaStreamWaitEvent(C->stream, ev, 0));
-    EC_CUDA(cudaEventDestroy(ev));
+  // ... and in the other direction: whatever the operands' own streams do next -- read the result,
+  // overwrite an input, release a pooled buffer in stream order -- comes after this product.
+  cudaEvent_t done = nullptr;
+  for (const ec_matrix *m : ops) {
+    if (m->stream == p->stream) continue;
+    if (!done) {
+      EC_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+      EC_CUDA(cudaEventRecord(done, p->stream));
+    }
+    EC_CUDA(cudaStreamWaitEvent(m->stream, done, 0));
   }
+  if (done) EC_CUDA(cudaEventDestroy(done));
   return EC_OK;
 }
 

@@ -19,6 +19,7 @@ struct ec_pipeline {
   StreamEngine *engine = nullptr;
   // workers for the matrix-at-a-time staging copies of copy_to_gpu / the conversion back
   // (created on the first pageable transfer of 1 MiB or more; EC_COMPAT_THREADS=0 disables)
+  bool mem_pool = false;   // device buffers of CudaMatrix come from the stream-ordered pool
   CopyPool *compat_pool = nullptr;
   bool compat_pool_tried = false;
   int cfg_chunk = 0, cfg_ring = 0, cfg_threads = 0;
@@ -51,6 +52,7 @@ struct ec_matrix {
   int64_t rows = 0, cols = 0;
   cudaStream_t stream = nullptr;
   int device = 0;
+  bool pooled = false;   // allocated with cudaMallocAsync on `stream` (freed in stream order)
 };
 
 namespace {

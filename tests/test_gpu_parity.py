@@ -363,6 +363,37 @@ def test_upload_download_bit_exact(pipe, shape):
     assert np.array_equal(dA.to_eigen(), B_copy)
 
 
+def test_matrices_constructed_inside_the_loop(pipe):
+    """Callers that build their CudaMatrix objects per iteration (allocation from the stream-ordered
+    pool, release in stream order behind the product that still reads them): results identical."""
+    n = 96
+    F = rnd(1, (n, n))
+    dF = ec.CudaMatrix(F, pipe.get_stream())
+    for i in range(300):
+        T = rnd(100 + i, (n, n))
+        dT = ec.CudaMatrix(T, pipe.get_stream())
+        dR = ec.CudaMatrix(n, n, pipe.get_stream())
+        pipe.gemm(dT, dF, dR)
+        dT.close()                       # freed while the product may still be running
+        if i % 37 == 0:
+            assert orc.rel_frobenius(dR.to_eigen(), orc.dgemm(T, F)) <= TOL
+        dR.close()
+
+
+def test_matrix_may_outlive_its_pipeline():
+    """The reference's deleter is a plain cudaFree (include/cudamatrix.hpp:46), so destroying the
+    pipeline first is tolerated there; here too, although the buffer belongs to the stream's pool."""
+    p = ec.CudaPipeline()
+    A = rnd(3, (64, 48))
+    dA = ec.CudaMatrix(A, p.get_stream())
+    assert np.array_equal(dA.to_eigen(), A)
+    p.close()
+    dA.close()
+    p2 = ec.CudaPipeline()
+    dB = ec.CudaMatrix(A, p2.get_stream())
+    assert np.array_equal(dB.to_eigen(), A)
+
+
 def test_copy_to_gpu_rejects_oversized_source(pipe):
     d = ec.CudaMatrix(3, 2, pipe.get_stream())
     with pytest.raises(RuntimeError):
