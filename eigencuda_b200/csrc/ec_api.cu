@@ -697,7 +697,17 @@ int ec_host_register(void *ptr, size_t bytes) {
   if (!ptr) return fail(EC_ERR_ARG, "null host pointer");
   cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
   if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    // Either the same range again (fine), or a small matrix that shares its first or last page
+    // with a pinned neighbour -- then the middle of it is NOT pinned and must not be taken for
+    // DMA-able.  Look at the pages (all of them up to 256, evenly spaced samples beyond).
     cudaGetLastError();
+    const uintptr_t lo = (uintptr_t)ptr & ~(uintptr_t)4095, hi = (uintptr_t)ptr + bytes - 1;
+    const size_t pages = (size_t)((hi - lo) / 4096) + 1, step = std::max<size_t>(1, pages / 256);
+    for (size_t pg = 0; pg < pages; pg += step)
+      if (!is_pinned_host((const void *)std::max(lo + pg * 4096, (uintptr_t)ptr)))
+        return fail(EC_ERR_ARG, "range overlaps a registered range without being covered by it");
+    if (!is_pinned_host((const void *)hi))
+      return fail(EC_ERR_ARG, "range overlaps a registered range without being covered by it");
     return EC_OK;
   }
   if (e != cudaSuccess) {
