@@ -170,8 +170,10 @@ int ec_host_free(void *ptr);
 /* Pin memory the caller already owns -- the storage of an Eigen::MatrixXd, a std::vector<double>
  * -- in place, so that copy_to_gpu, the conversion back and ec_tensor_stream_run move it by DMA
  * without a staging copy.  The range must stay allocated until
- * ec_host_unregister.  Registering costs about a millisecond per 16 MiB: worth it for buffers
- * that are reused, not for one transfer.  Zero bytes or an already-pinned range is EC_OK. */
+ * ec_host_unregister.  Registering is expensive -- measured on the B200 box: 3 ms for 2 MiB,
+ * 30 ms for 32 MiB, not faster from several threads (tools/register_probe.py) -- which is why
+ * the library stages pageable memory instead of pinning it on the fly: worth it only for
+ * buffers that are reused many times.  Zero bytes or an already-pinned range is EC_OK. */
 int ec_host_register(void *ptr, size_t bytes);
 int ec_host_unregister(void *ptr);
 /* x = 2u-1, u in [0,1): splitmix64 on (seed, matrix_id, column-major index); bit-identical to
