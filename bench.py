@@ -397,6 +397,36 @@ def main():
     if world == 1 and not args.no_extras:
         extras = {}
         torch.cuda.empty_cache()
+        # skinny shapes are HBM-bound, not DMMA-bound: achieved GB/s over the algorithmic bytes
+        # (A and B read once, C written once) against the measured HBM peak
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            hbm_peak = 6458.4   # B200_PROFILING.md fallback
+        skinny = []
+        for (sm_, sn_, sk_) in ((1 << 20, 32, 32), (1 << 20, 16, 128), (1 << 20, 128, 16), (8192, 8192, 64)):
+            A = torch.empty(sm_ * sk_, dtype=torch.float64, device=dev)
+            B = torch.empty(sk_ * sn_, dtype=torch.float64, device=dev)
+            Cm = torch.empty(sm_ * sn_, dtype=torch.float64, device=dev)
+            pipe.fill_uniform(SEED, 0, A.data_ptr(), sm_ * sk_, 1)
+            pipe.fill_uniform(SEED, 1, B.data_ptr(), sk_ * sn_, 1)
+            best = float("inf")
+            for it in range(8):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                pipe.dgemm(0, 0, sm_, sn_, sk_, 1.0, A.data_ptr(), sm_, B.data_ptr(), sk_, 0.0, Cm.data_ptr(), sm_)
+                b.record(stream)
+                b.synchronize()
+                if it >= 3:
+                    best = min(best, a.elapsed_time(b))
+            nbytes = 8.0 * (sm_ * sk_ + sk_ * sn_ + sm_ * sn_)
+            skinny.append({"m": sm_, "n": sn_, "k": sk_, "ms": best, "hbm_gbs": nbytes / best / 1e6,
+                           "frac_of_hbm_peak": nbytes / best / 1e6 / hbm_peak,
+                           "tflops": 2.0 * sm_ * sn_ * sk_ / best / 1e9, "kernel": pipe.last_kernel()})
+            del A, B, Cm
+        extras["skinny_hbm_bound"] = {"hbm_peak_gbs": hbm_peak, "shapes": skinny,
+                                      "note": "each shape moves 0.5-1.2 GB per call, far more than the 126 MB L2 holds"}
+        torch.cuda.empty_cache()
         # configs[3]: 2000 x (1000x1000): A^T * B_i and A^T * M_i * A, resident in HBM
         n4, c4 = 1000, 2000
         F4 = torch.empty(n4 * n4, dtype=torch.float64, device=dev)

