@@ -370,7 +370,7 @@ def main():
         sweep = []
         del T, R
         torch.cuda.empty_cache()
-        for nn in (512, 1024, 2048, 4096, 8192, 16384):
+        for nn in (256, 512, 1024, 2048, 4096, 8192, 16384):
             A = torch.empty(nn * nn, dtype=torch.float64, device=dev)
             B = torch.empty(nn * nn, dtype=torch.float64, device=dev)
             Cm = torch.empty(nn * nn, dtype=torch.float64, device=dev)
@@ -389,6 +389,7 @@ def main():
                 best = min(best, a.elapsed_time(b))
             tf = 2.0 * nn ** 3 / (best * 1e-3) / 1e12
             sweep.append({"n": nn, "ms": best, "tflops": tf, "frac_of_datasheet_fp64": tf / FP64_DATASHEET_TFLOPS,
+                          "hbm_gbs": 24.0 * nn * nn / best / 1e6,   # algorithmic: read A and B, write C
                           "kernel": pipe.last_kernel()})
             del A, B, Cm
 

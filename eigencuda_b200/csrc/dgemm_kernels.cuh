@@ -30,6 +30,8 @@ namespace ec {
 // Tile configurations of the hot kernel
 // ------------------------------------------------------------------------------------------
 constexpr int BK = 16;  // k extent per stage: 16 doubles = 128 B = one swizzle span
+constexpr int SK_TREE_MIN = 8;     // stream-K: more contributors to one tile than this -> two-level sum
+constexpr int SK_TREE_GROUP = 16;  // ... in groups of this many consecutive ranks
 
 // One CTA computes a BM x BN tile of C with (BM/WM) x (BN/WN) consumer warps, each holding a
 // WM x WN sub-tile in registers, plus one producer warpgroup (its first warp's elected lane issues
@@ -426,27 +428,24 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
     // thing this CTA computes).  The segment that starts a tile but does not finish it (always
     // the last thing this CTA computes in the region) owns the tile: it adds, in CTA order, the
     // partials of the CTAs that follow it -- published long before -- and writes C.
-    if (sg.kb0 != 0) {
+    //
+    // Deep splits (a 64 x 64 product over K = 10^6 is cut over every CTA of the grid) would make
+    // that a serial chain of hundreds of dependent workspace reads in ONE CTA.  Beyond
+    // SK_TREE_MIN contributors the sum is therefore taken in two levels: the contributors form
+    // groups of SK_TREE_GROUP consecutive ranks, the first of each group adds its followers'
+    // partials to its own before publishing, and the owner adds the group sums.  Followers never
+    // wait, leaders wait only for followers, the owner only for leaders: no cycle; the order of
+    // additions is fixed by the ranks, so results stay bit-reproducible.
+    if (sg.kb0 != 0 || sg.kb1 != kblocks) {
+      const int64_t S = p.sk_tiles * (int64_t)kblocks;
+      const int64_t G = gridDim.x;
       const unsigned rank = Schedule::sk_rank(p);
-      double *ws = p.sk_workspace + (size_t)rank * (BM * BN) + threadIdx.x;
-#pragma unroll
-      for (int i = 0; i < MB; ++i)
-#pragma unroll
-        for (int j = 0; j < NB; ++j)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) __stcg(ws + ((i * NB + j) * 2 + e) * CONSUMER_THREADS, acc[i][j][e]);
-      __threadfence();
-      consumer_bar_sync(CONSUMER_THREADS);
-      if (threadIdx.x == 0) st_release_gpu(p.sk_flags + rank, p.sk_epoch);
-      continue;
-    }
-    if (sg.kb1 != kblocks) {
-      const int64_t S = p.sk_tiles * kblocks;
-      const int64_t tile_end = (sg.tile + 1) * (int64_t)kblocks;
-      int covered = sg.kb1;
-      for (unsigned d = Schedule::sk_rank(p) + 1; covered < kblocks; ++d) {
-        const int64_t d0 = S * d / gridDim.x, d1 = S * (d + 1) / gridDim.x;
-        if (d1 == d0) continue;  // CTA d has no stream-K work (S < gridDim.x): nothing to wait for
+      const int64_t t0 = sg.tile * (int64_t)kblocks, t1 = t0 + kblocks;
+      // first and last rank whose run [S*d/G, S*(d+1)/G) meets this tile (runs are non-empty when S >= G)
+      const unsigned owner = (unsigned)(((t0 + 1) * G + S - 1) / S - 1);
+      const unsigned last = (unsigned)((t1 * G + S - 1) / S - 1);
+      const bool tree = S >= G && last - owner > (unsigned)SK_TREE_MIN;
+      auto add_partial = [&](unsigned d) {
         if (threadIdx.x == 0) {
           while (ld_acquire_gpu(p.sk_flags + d) != p.sk_epoch) {
           }
@@ -459,7 +458,34 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
           for (int j = 0; j < NB; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) acc[i][j][e] += __ldcg(ws + ((i * NB + j) * 2 + e) * CONSUMER_THREADS);
-        covered += (int)((d1 < tile_end ? d1 : tile_end) - d0);
+      };
+      if (sg.kb0 != 0) {
+        if (tree && (rank - owner - 1) % SK_TREE_GROUP == 0) {   // group leader
+          const unsigned group_last = min(rank + SK_TREE_GROUP - 1, last);
+          for (unsigned d = rank + 1; d <= group_last; ++d) add_partial(d);
+        }
+        double *ws = p.sk_workspace + (size_t)rank * (BM * BN) + threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) __stcg(ws + ((i * NB + j) * 2 + e) * CONSUMER_THREADS, acc[i][j][e]);
+        __threadfence();
+        consumer_bar_sync(CONSUMER_THREADS);
+        if (threadIdx.x == 0) st_release_gpu(p.sk_flags + rank, p.sk_epoch);
+        continue;
+      }
+      if (tree) {
+        for (unsigned d = rank + 1; d <= last; d += SK_TREE_GROUP) add_partial(d);
+      } else {
+        int covered = sg.kb1;
+        for (unsigned d = rank + 1; covered < kblocks; ++d) {
+          const int64_t d0 = S * d / G, d1 = S * (d + 1) / G;
+          if (d1 == d0) continue;  // CTA d has no stream-K work (S < gridDim.x): nothing to wait for
+          add_partial(d);
+          covered += (int)((d1 < t1 ? d1 : t1) - d0);
+        }
       }
     }
 

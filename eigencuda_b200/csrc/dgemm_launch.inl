@@ -217,9 +217,14 @@ TileChoice choose_tile(const ec_pipeline *p, int64_t m, int64_t n, int64_t k, in
       const double tile_clk_sk = (double)c.bm * c.bn * kpad / 64.0 / c.eff[c.ctas - 1] + c.overhead;
       // with far fewer tiles than CTAs a tile is cut into several partials and its owner adds
       // them one after the other: the exposed tail grows with the partials per tile
+      // (beyond SK_TREE_MIN partials the kernel sums in two levels: a group of SK_TREE_GROUP,
+      // then the group sums)
       const double splits = std::max(1.0, (double)slots / (double)tiles);
+      const double chain = splits <= (double)ec::SK_TREE_MIN
+                               ? splits
+                               : (double)ec::SK_TREE_GROUP + splits / (double)ec::SK_TREE_GROUP;
       const double sk = force_sk ? dp * 1e-3
-                                 : (double)tiles / sms * tile_clk_sk + c.fixup * (1.0 + 0.35 * (splits - 1.0));
+                                 : (double)tiles / sms * tile_clk_sk + c.fixup * (1.0 + 0.35 * (chain - 1.0));
       if (sk < best) { best = sk; pick = {c.id, true}; }
     }
   }

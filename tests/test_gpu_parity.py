@@ -239,6 +239,32 @@ def test_stream_k_schedule(pipe, tile, ta, tb, monkeypatch):
     assert orc.rel_frobenius(got0, want) <= TOL
 
 
+@pytest.mark.parametrize("tile", [1, 2, 3])
+@pytest.mark.parametrize("shape", [(64, 64, 200000), (128, 96, 120000), (200, 40, 70000)])
+def test_stream_k_deep_split_two_level_sum(pipe, tile, shape, monkeypatch):
+    """Inner-product shapes: a handful of output tiles, K in the hundred thousands, so every CTA
+    of the grid contributes to the same tile.  Beyond 8 contributors the fix-up sums in two levels
+    (groups of 16 ranks); same bar against the long-double oracle, bit-reproducible run to run."""
+    monkeypatch.setenv("EC_FORCE_TILE", str(tile))
+    m, n, k = shape
+    A, B = rnd(k, (m, k)), rnd(k + 1, (k, n))
+    dA, dB = ec.CudaMatrix(A, pipe.get_stream()), ec.CudaMatrix(B, pipe.get_stream())
+    dC = ec.CudaMatrix(m, n, pipe.get_stream())
+    pipe.gemm(dA, dB, dC)
+    assert pipe.last_kernel().endswith("_sk"), pipe.last_kernel()
+    got = dC.to_eigen()
+    want = orc.dgemm(A, B, flavour="ld")
+    assert orc.rel_frobenius(got, want) <= TOL
+    pipe.gemm(dA, dB, dC)
+    assert np.array_equal(dC.to_eigen(), got)
+    # transposed operands (K-major A, MN-major B) through the raw entry
+    dAt = ec.CudaMatrix(np.asfortranarray(A.T), pipe.get_stream())
+    dBt = ec.CudaMatrix(np.asfortranarray(B.T), pipe.get_stream())
+    pipe.dgemm(1, 1, m, n, k, 1.0, dAt.data(), k, dBt.data(), n, 0.0, dC.data(), m)
+    assert pipe.last_kernel().endswith("_sk"), pipe.last_kernel()
+    assert orc.rel_frobenius(dC.to_eigen(), want) <= TOL
+
+
 def test_slot_release_race_regression(pipe, monkeypatch):
     """Regression: with several CTAs per SM, a consumer's empty-barrier arrive used to be able
     to overtake its own in-flight LDS (queued behind another CTA's epilogue stores), letting the
