@@ -50,7 +50,10 @@ int dgemm_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
   // a small tile's worth of work.  Skinny ones (a million rows by 16 columns) count: they are
   // HBM-bound, TMA zero-fills the part of the box that hangs over the edge, and the padded DMMA
   // work is free (5.2 TB/s there against 0.7 TB/s from the SIMT kernel).
-  const bool big_enough = (m >= 8 && n >= 8 && k >= 8) && (m * n * k >= (int64_t)64 * 64 * 64);
+  // A batch counts as a whole: a tensor of 10^5 matrices of 32 x 32 is one HBM-bound job, not
+  // 10^5 tiny ones.
+  const bool big_enough = (m >= 8 && n >= 8 && k >= 8) &&
+                          ((double)m * (double)n * (double)k * (double)batch >= 64.0 * 64.0 * 64.0);
   const bool c_ok = m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31);
   if (big_enough && c_ok && tma_ok(oa, batch) && tma_ok(ob, batch)) {
     static const char *const nL[8] = {"tma_dmma_TN", "tma_dmma_TT", "tma_dmma_NN", "tma_dmma_NT",
@@ -59,9 +62,12 @@ int dgemm_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
                                       "tma_dmma_TN_s_sk", "tma_dmma_TT_s_sk", "tma_dmma_NN_s_sk", "tma_dmma_NT_s_sk"};
     static const char *const nX[8] = {"tma_dmma_TN_xs", "tma_dmma_TT_xs", "tma_dmma_NN_xs", "tma_dmma_NT_xs",
                                       "tma_dmma_TN_xs_sk", "tma_dmma_TT_xs_sk", "tma_dmma_NN_xs_sk", "tma_dmma_NT_xs_sk"};
+    static const char *const nT[8] = {"tma_dmma_TN_t", "tma_dmma_TT_t", "tma_dmma_NN_t", "tma_dmma_NT_t",
+                                      "tma_dmma_TN_t_sk", "tma_dmma_TT_t_sk", "tma_dmma_NN_t_sk", "tma_dmma_NT_t_sk"};
     const TileChoice ch = choose_tile(p, m, n, k, batch);
     switch (ch.tile) {
       case TILE_S: return run_tma_dmma<ec::CfgS>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nS);
+      case TILE_T: return run_tma_dmma<ec::CfgT>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nT);
       case TILE_XS: return run_tma_dmma<ec::CfgXS>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nX);
       default: return run_tma_dmma<ec::CfgL>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nL);
     }

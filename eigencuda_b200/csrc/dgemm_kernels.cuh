@@ -69,6 +69,7 @@ struct TileCfg {
 using CfgL  = TileCfg<128, 128, 64, 32, 5, 1, true>;    // 8 consumer warps, 160 KiB, 232 regs (6 stages measured: no gain)
 using CfgS  = TileCfg< 64,  64, 32, 32, 4, 2, false>;   // 4 consumer warps,  64 KiB, 2 CTAs/SM
 using CfgXS = TileCfg< 64,  32, 32, 16, 4, 3, false>;   // 4 consumer warps,  48 KiB, 3 CTAs/SM
+using CfgT  = TileCfg< 32,  32, 16, 16, 4, 5, false>;   // 4 consumer warps,  33 KiB, 5 CTAs/SM (80 regs; 6 would spill): tensors of matrices of 32 x 32 and less
 // (A 128x64 / 2 CTAs-per-SM variant and register-split variants of the small tiles were measured
 //  and lost everywhere -- profiles/r01_tile_sweep*.json -- so they are not built.)
 

@@ -173,7 +173,7 @@ int run_tma_dmma(ec_pipeline *p, const Operand &oa, const Operand &ob, int64_t m
 // does ceil(tiles / SMs) tiles, under stream-K every SM does tiles / SMs of them plus one
 // workspace round trip -- and (b) per-tile overhead and main-loop efficiency, which get worse
 // as tiles shrink.  Cost model in SM clocks, fitted to profiles/r01_tile_sweep*.json.
-enum { TILE_AUTO = 0, TILE_L = 1, TILE_S = 2, TILE_XS = 3 };
+enum { TILE_AUTO = 0, TILE_L = 1, TILE_S = 2, TILE_XS = 3, TILE_T = 4 };
 
 struct TileChoice { int tile; bool sk; };
 
@@ -192,16 +192,20 @@ TileChoice choose_tile(const ec_pipeline *p, int64_t m, int64_t n, int64_t k, in
   // badly until a second or third CTA shares the SM); overhead: exposed clocks per tile; fixup:
   // exposed clocks of one stream-K tail (publish partial, wait, read, epilogue).  Fitted to
   // profiles/r01_tile_sweep*.json and profiles/r01_small_probe.txt (back-to-back launches).
-  struct Cand { int id, bm, bn, ctas; double eff[3], overhead, fixup; };
-  const Cand cands[3] = {{TILE_L, 128, 128, 1, {0.987, 0.987, 0.987}, 2300.0, 30000.0},
-                         {TILE_S, 64, 64, 2, {0.59, 0.955, 0.955}, 1200.0, 17000.0},
-                         {TILE_XS, 64, 32, 3, {0.50, 0.76, 0.80}, 800.0, 20000.0}};
+  // The 32x32 tile needs 4 flop per operand byte from L2, more than L2 delivers at the full DMMA
+  // rate: it tops out near 0.72 however many CTAs share the SM (26-30 TFLOP/s), but it is the only
+  // shape that fills the machine for n <= 640 and wastes nothing on matrices of 32 x 32 and less.
+  struct Cand { int id, bm, bn, ctas; double eff[6], overhead, fixup; };
+  const Cand cands[4] = {{TILE_L, 128, 128, 1, {0.987, 0.987, 0.987, 0.987, 0.987, 0.987}, 2300.0, 30000.0},
+                         {TILE_S, 64, 64, 2, {0.59, 0.955, 0.955, 0.955, 0.955, 0.955}, 1200.0, 17000.0},
+                         {TILE_XS, 64, 32, 3, {0.50, 0.76, 0.80, 0.80, 0.80, 0.80}, 450.0, 20000.0},
+                         {TILE_T, 32, 32, 5, {0.30, 0.58, 0.68, 0.72, 0.72, 0.72}, 250.0, 20000.0}};
   const double kpad = (double)((k + 15) / 16 * 16);
   const int64_t kblocks = (k + 15) / 16;
   double best = 1e300;
   TileChoice pick{TILE_L, false};
   for (const Cand &c : cands) {
-    if (force >= TILE_L && force <= TILE_XS && c.id != force) continue;
+    if (force >= TILE_L && force <= TILE_T && c.id != force) continue;
     const int64_t tiles = ((m + c.bm - 1) / c.bm) * ((n + c.bn - 1) / c.bn) * batch;
     const int sms = p->sm_count - p->sm_margin;
     const int64_t slots = (int64_t)sms * c.ctas;

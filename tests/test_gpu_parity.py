@@ -206,20 +206,20 @@ def test_dgemm_simt_kernel_odd_shapes(pipe, ta, tb, shape):
     assert orc.rel_frobenius(got, want) <= TOL
 
 
-@pytest.mark.parametrize("tile", [1, 2, 3])
+@pytest.mark.parametrize("tile", [1, 2, 3, 4])
 @pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
 def test_every_tile_configuration(pipe, tile, ta, tb, monkeypatch):
-    """The three CTA tile shapes (128x128, 64x64, 64x32) compute the same product."""
+    """The four CTA tile shapes (128x128, 64x64, 64x32, 32x32) compute the same product."""
     monkeypatch.setenv("EC_FORCE_TILE", str(tile))
     for (m, n, k) in [(256, 192, 144), (130, 70, 50), (520, 264, 1030)]:
         got, want = run_dgemm(pipe, ta, tb, m, n, k, 1.25, -0.5, seed=tile + m)
-        suffix = {1: "", 2: "_s", 3: "_xs"}[tile]
+        suffix = {1: "", 2: "_s", 3: "_xs", 4: "_t"}[tile]
         name = "tma_dmma_" + ("T" if ta else "N") + ("T" if tb else "N") + suffix
         assert pipe.last_kernel() in (name, name + "_sk")
         assert orc.rel_frobenius(got, want) <= TOL
 
 
-@pytest.mark.parametrize("tile", [1, 2, 3])
+@pytest.mark.parametrize("tile", [1, 2, 3, 4])
 @pytest.mark.parametrize("ta,tb", [(False, False), (True, True)])
 def test_stream_k_schedule(pipe, tile, ta, tb, monkeypatch):
     """Shapes whose tile count does not fill the last wave take the stream-K schedule: partial
@@ -239,7 +239,7 @@ def test_stream_k_schedule(pipe, tile, ta, tb, monkeypatch):
     assert orc.rel_frobenius(got0, want) <= TOL
 
 
-@pytest.mark.parametrize("tile", [1, 2, 3])
+@pytest.mark.parametrize("tile", [1, 2, 3, 4])
 @pytest.mark.parametrize("shape", [(64, 64, 200000), (128, 96, 120000), (200, 40, 70000)])
 def test_stream_k_deep_split_two_level_sum(pipe, tile, shape, monkeypatch):
     """Inner-product shapes: a handful of output tiles, K in the hundred thousands, so every CTA
@@ -287,7 +287,7 @@ def test_slot_release_race_regression(pipe, monkeypatch):
     want = run(1)
     F = orc.fill_uniform(orc.SEED, 0, (n, n))
     assert orc.rel_frobenius(want[:, :n], orc.cpu_product(orc.fill_uniform(orc.SEED, 1, (n, n)), F)) <= TOL
-    for tile in (2, 3):
+    for tile in (2, 3, 4):
         for _ in range(4):
             assert np.array_equal(run(tile), want), f"tile configuration {tile} diverged"
 
@@ -324,6 +324,23 @@ def test_one_cta_per_tile_schedule(pipe):
     pipe.set_schedule(stream_k=True, one_cta_per_tile=False)
     assert np.array_equal(got, want)
     assert orc.rel_frobenius(got, orc.cpu_product(A, B)) <= TOL
+
+
+@pytest.mark.parametrize("kind", ["right", "left", "left_t", "basis"])
+@pytest.mark.parametrize("n", [8, 16, 24, 32, 48])
+def test_tensor_of_tiny_matrices_resident(pipe, kind, n):
+    """A tensor of matrices smaller than the smallest tile: the batch as a whole decides the
+    kernel (one HBM-bound job), each matrix is one partly empty tile; every stream kind."""
+    count = 777
+    F = orc.fill_uniform(orc.SEED, 0, (n, n))
+    ts = [orc.fill_uniform(orc.SEED, i + 1, (n, n)) for i in range(count)]
+    code = {"right": ec.EC_STREAM_RIGHT, "left": ec.EC_STREAM_LEFT, "left_t": ec.EC_STREAM_LEFT_T,
+            "basis": ec.EC_STREAM_BASIS}[kind]
+    res = pipe.tensor_stream(code, F, ts)
+    assert pipe.last_kernel().startswith("tma_dmma"), pipe.last_kernel()
+    want = orc.tensor_stream(kind, F, ts, flavour="fast")
+    for r, w in zip(res, want):
+        assert orc.rel_frobenius(r, w) <= TOL
 
 
 def test_beta_zero_ignores_nan_in_c(pipe):
