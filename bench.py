@@ -617,5 +617,16 @@ def main():
         dist.destroy_process_group()
 
 
+def _emit_only_the_json_line():
+    """The contract is ONE line on stdout.  Libraries write banners to file descriptor 1 behind
+    Python's back (NCCL prints its version there at init): point fd 1 at stderr for the whole run
+    and give print() a handle on the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _emit_only_the_json_line()
     main()

@@ -170,3 +170,29 @@ def test_copy_pool_stress(tmp_path):
                     "-o", exe], check=True)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=240)
     assert out.returncode == 0 and "ALL PASSED" in out.stdout, out.stdout + out.stderr
+
+
+# ---------------------------------------------------------------------------------------------
+# bench.py contract that can be checked without a GPU: ONE JSON line on stdout
+# ---------------------------------------------------------------------------------------------
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["value"] > 0
+    for key in ("metric", "unit", "n_gpus", "steps", "warmup", "higher_is_better", "config", "cpu_baseline", "e2e"):
+        assert key in line
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    # under torchrun only rank 0 runs it; the other ranks exit 0 without output
+    env.update({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
