@@ -54,6 +54,7 @@ SIGNATURES = {
     "ec_pipeline_set_stream_config": (_int, [_vp, _int, _int, _int]),
     "ec_host_alloc": (_int, [C.c_size_t, C.POINTER(_vp)]),
     "ec_host_free": (_int, [_vp]),
+    "ec_plan_dgemm": (_int, [_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_int), C.POINTER(_int)]),
     "ec_host_register": (_int, [_vp, C.c_size_t]),
     "ec_host_unregister": (_int, [_vp]),
     "ec_fill_uniform": (_int, [_vp, _u64, _u64, _dp, _i64]),

@@ -233,6 +233,14 @@ class CudaPipeline:
             pass
 
 
+def plan_dgemm(m, n, k, batch=1, sm_count=148):
+    """(tile, stream_k) the dispatcher's cost model picks: tile 1 = 128x128, 2 = 64x64, 3 = 64x32,
+    4 = 32x32.  Needs no device (ec_plan_dgemm)."""
+    tile, sk = C.c_int(), C.c_int()
+    check(lib.ec_plan_dgemm(int(sm_count), int(m), int(n), int(k), int(batch), C.byref(tile), C.byref(sk)))
+    return tile.value, bool(sk.value)
+
+
 def result_shape(kind, f_shape, t_shape):
     """Shape of one result of a tensor-stream job; raises like the reference's gemm on an inner
     dimension mismatch (reference src/cudapipeline.cc:26-28)."""

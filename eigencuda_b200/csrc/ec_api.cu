@@ -183,6 +183,17 @@ int ec_pipeline_set_sm_margin(ec_pipeline *p, int sms) {
   p->sm_margin = sms;
   return EC_OK;
 }
+int ec_plan_dgemm(int sm_count, int64_t m, int64_t n, int64_t k, int64_t batch, int *tile,
+                  int *stream_k) {
+  if (!tile || !stream_k) return fail(EC_ERR_ARG, "null out pointer");
+  if (sm_count <= 0 || m <= 0 || n <= 0 || k <= 0 || batch <= 0) return fail(EC_ERR_ARG, "bad planning query");
+  ec_pipeline model;   // host-side description only: no stream, nothing allocated
+  model.sm_count = sm_count;
+  const TileChoice ch = choose_tile(&model, m, n, k, batch);
+  *tile = ch.tile;
+  *stream_k = ch.sk ? 1 : 0;
+  return EC_OK;
+}
 int64_t ec_pipeline_launch_count(const ec_pipeline *p) { return p ? p->launches : 0; }
 const char *ec_pipeline_last_kernel(const ec_pipeline *p) { return p ? p->last_kernel : "none"; }
 

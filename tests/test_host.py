@@ -196,3 +196,43 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=240, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+# ---------------------------------------------------------------------------------------------
+# the dispatcher's cost model, queried without a device: the choices that were measured best on
+# a B200 (profiles/r01_small_probe.txt, r01_batched_small_probe.txt, r01_skinny_probe.txt) stay put
+# ---------------------------------------------------------------------------------------------
+L, S, XS, T = 1, 2, 3, 4
+
+
+@pytest.mark.parametrize("shape,expected", [
+    ((512, 512, 512, 4096), (L, False)),        # the bench workload: whole 128x128 tiles
+    ((8192, 8192, 8192, 1), (L, True)),         # big square: stream-K evens out the last wave
+    ((2048, 2048, 2048, 1), (L, True)),
+    ((1024, 1024, 1024, 1), (S, True)),
+    ((768, 768, 768, 1), (XS, False)),
+    ((512, 512, 512, 1), (T, False)),           # small squares: only the 32x32 tile fills 148 SMs
+    ((256, 256, 256, 1), (T, False)),
+    ((32, 32, 32, 131072), (T, False)),         # tensors of tiny matrices
+    ((16, 16, 16, 524288), (T, False)),
+    ((64, 64, 64, 32768), (S, False)),
+    ((96, 96, 96, 14563), (T, False)),
+    ((128, 128, 128, 8192), (L, False)),
+    ((64, 64, 1 << 20, 1), (S, True)),          # inner-product shape: stream-K over the whole grid
+    ((1 << 20, 32, 32, 1), (XS, False)),        # tall and skinny: HBM-bound
+    ((1 << 20, 16, 128, 1), (XS, False)),
+    ((1 << 20, 128, 16, 1), (L, False)),
+])
+def test_cost_model_choices(shape, expected, monkeypatch):
+    monkeypatch.delenv("EC_FORCE_TILE", raising=False)
+    monkeypatch.delenv("EC_STREAM_K", raising=False)
+    assert ec.plan_dgemm(*shape) == expected
+
+
+def test_cost_model_overrides(monkeypatch):
+    monkeypatch.setenv("EC_FORCE_TILE", "2")
+    assert ec.plan_dgemm(8192, 8192, 8192)[0] == S
+    monkeypatch.setenv("EC_STREAM_K", "0")
+    assert ec.plan_dgemm(8192, 8192, 8192) == (S, False)
+    with pytest.raises(ec.EigenCudaError):
+        ec.plan_dgemm(0, 8, 8)
