@@ -561,6 +561,18 @@ def main():
                                           "matrices_per_s_min_max": [rates[0], rates[-1]], "repeats": len(rates),
                                           "what": "README.md:62-66 loop through CudaMatrix/CudaPipeline of this repo, unchanged caller code"}
         del Tsrc, base, outs, ts_h
+        # the same three ways of driving the library from C++ caller code (examples/readme_loop.cc,
+        # compiled against include/*.hpp by __graft_entry__.build())
+        exe = os.path.join(ROOT, "tools", "bin", "readme_loop")
+        if os.path.exists(exe):
+            try:
+                res = subprocess.run([exe, str(n), "256"], capture_output=True, text=True, timeout=180)
+                if res.returncode == 0:
+                    extras["cpp_readme_loop"] = json.loads(res.stdout.strip().splitlines()[-1])
+                else:
+                    extras["cpp_readme_loop"] = {"error": (res.stderr or res.stdout)[-300:]}
+            except Exception as exc:   # a reported extra, never a reason to lose the bench line
+                extras["cpp_readme_loop"] = {"error": repr(exc)[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
