@@ -59,11 +59,36 @@ def parse():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-peaks", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--ref-sample", type=int, default=512, help="matrices per step for --impl reference")
+    ap.add_argument("--ref-sample", type=int, default=0, help="matrices per step for --impl reference (0 = the e2e leg's count at N=1)")
     ap.add_argument("--no-extras", action="store_true", help="skip configs[3] (transposed / basis transform) and the pageable e2e")
     ap.add_argument("--chunk", type=int, default=0, help="tensor-stream engine: matrices per device chunk (0 = default)")
     ap.add_argument("--ring", type=int, default=0, help="tensor-stream engine: ring depth (0 = default)")
     return ap.parse_args()
+
+
+E2E_TOTAL_CAP = 8192   # matrices in the e2e tensor over all GPUs: 16 GiB each way of pinned host memory at 512^2
+
+
+def e2e_matrices_per_gpu(args, world):
+    """Tensor elements per GPU in the end-to-end legs.  The resident leg keeps --count per GPU; the
+    host-memory legs cap the WHOLE tensor at E2E_TOTAL_CAP matrices (pinned host memory is the
+    scarce resource, and a step stays hundreds of milliseconds long at every N)."""
+    if args.e2e_count:
+        return args.e2e_count
+    return max(64, min(args.count, E2E_TOTAL_CAP * 512 * 512 // (args.n * args.n) // world))
+
+
+def make_config(args, world):
+    """One description of the workload for BOTH arms (ours and --impl reference)."""
+    n, count = args.n, args.count
+    return {"workload": f"tensor_stream_right (BASELINE.json configs[2]): R_i = T_i({n}x{n}) * F({n}x{n}), FP64 "
+                        f"column-major, one fixed F, the reference's streaming pattern (README.md:58-66)",
+            "n": n, "kind": "right", "matrices_per_gpu": count,
+            "e2e_matrices_per_gpu": e2e_matrices_per_gpu(args, world),
+            "parallelism": f"tensor sharded over {world} GPU(s) in contiguous index ranges, fixed operand "
+                           f"broadcast once (NCCL), no result exchange",
+            "l2": f"inputs {count * n * n * 8 / 2**30:.1f} GiB per step per GPU > 126 MB L2; no flush needed",
+            "generator": "splitmix64 counter-based, seed 20200210"}
 
 
 class ClockSampler:
@@ -157,15 +182,19 @@ def reference_arm(args, rank, world):
         return
     import numpy as np
     from oracle import oracle_py as orc
-    n, cnt = args.n, args.ref_sample
+    n = args.n
+    # the same tensor our e2e leg streams at N = 1 (the reference has one GPU however many the box has)
+    cnt = args.ref_sample or e2e_matrices_per_gpu(args, 1)
     line = {"impl": "reference", "metric": "tensor_stream_matrices_per_s", "unit": "matrices/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"tensor_stream_right: T_i({n}x{n}) * F({n}x{n}), FP64 col-major",
-                       "matrices_per_step": cnt, "kind": "right"}}
+            "data": "synthetic", "config": make_config(args, world)}
     F = orc.fill_uniform(SEED, 0, (n, n))
-    ts = [orc.fill_uniform(SEED, i + 1, (n, n)) for i in range(cnt)]
+    # the tensor as ONE pageable block (what a std::vector<Eigen::MatrixXd> is: pageable heap memory)
+    base = np.empty((n * n, cnt), dtype=np.float64, order="F")
+    for i in range(cnt):
+        base[:, i] = orc.fill_uniform(SEED, i + 1, (n, n)).reshape(-1, order="F")
+    ptrs = (C.c_void_p * cnt)(*[base.ctypes.data + 8 * n * n * i for i in range(cnt)])
     use_ref = False
     if orc.Reference.available():
         try:
@@ -175,21 +204,23 @@ def reference_arm(args, rank, world):
             use_ref = False
     times = []
     if use_ref:
-        for i in range(args.warmup + args.steps):
-            _, sec = ref.tensor_stream(0, F, ts)
-            if i >= args.warmup:
-                times.append(sec)
+        secs, got = ref.tensor_stream_steps(0, F, ptrs, cnt, (n, n), args.warmup, args.steps, check_index=cnt // 3)
+        times = secs
+        want = orc.cpu_product(base[:, cnt // 3].reshape(n, n, order="F"), F)
+        if not orc.rel_frobenius(got, want) <= 1e-12:
+            raise SystemExit("bench.py --impl reference: the reference's result fails the parity check")
         kind, cores = "reference", 1
-        sample = (f"{cnt} matrices per step through the unmodified reference loop (copy_to_gpu -> gemm "
+        sample = (f"{cnt} matrices per step (the e2e leg's tensor at N=1) through the unmodified reference loop (copy_to_gpu -> gemm "
                   f"-> convert, README.md:62-66): cuBLAS {n}^3 DGEMM on the same B200, pageable host "
                   f"memory, one host thread (rank 0 only: the reference has no multi-GPU path)")
         bytes_in, bytes_out = cnt * n * n * 8, cnt * n * n * 8
     else:
+        sub = max(16, cnt // 8)
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            for t in ts[: max(16, cnt // 8)]:
-                orc.cpu_product(t, F)
-            sec = (time.perf_counter() - t0) * cnt / max(16, cnt // 8)
+            for j in range(sub):
+                orc.cpu_product(base[:, j].reshape(n, n, order="F"), F)
+            sec = (time.perf_counter() - t0) * cnt / sub
             if i >= args.warmup:
                 times.append(sec)
         kind, cores = "port", len(os.sched_getaffinity(0))
@@ -204,6 +235,125 @@ def reference_arm(args, rank, world):
                          "d2h_bytes_per_step": bytes_out},
                  "gpu_launches": 0})
     print(json.dumps(line), flush=True)
+
+
+def mem_available_bytes():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    return None
+
+
+def e2e_legs(args, ec, orc, pipe, torch, dev, world, Fh):
+    """End to end through the reference-facing call, host buffers, H2D + D2H of every matrix inside
+    the timed region.  Returns (e2e from pinned host memory, e2e from pageable host memory).
+
+    N = 1: ec_tensor_stream_run.  N > 1: ec_tensor_stream_run_multi -- one process, the library's own
+    scheduler: contiguous shards of the ONE vector, one worker thread + pinned ring + three streams
+    per GPU, F uploaded once and broadcast with NCCL every call, results DMA'd into results[i].
+    Before the legs the host-link ceiling of THIS box is measured with plain pinned copies on the
+    same GPUs at once (ec_host_link_probe); frac_of_link = achieved / that ceiling."""
+    import numpy as np
+    n, elems = args.n, args.n * args.n
+    mbytes = elems * 8
+    devices = list(range(world))
+    per_gpu = e2e_matrices_per_gpu(args, world)
+    total = per_gpu * world
+    note = None
+    avail = mem_available_bytes()
+    if avail is not None and 2 * total * mbytes > 0.6 * avail:      # both buffers pinned at once
+        total = max(64 * world, int(0.6 * avail / (2 * mbytes)) // world * world)
+        note = (f"e2e tensor reduced to {total} matrices: 2 x {total * mbytes / 2**30:.1f} GiB of pinned host memory "
+                f"is 60 % of MemAvailable ({avail / 2**30:.0f} GiB)")
+        per_gpu = total // world
+    link = ec.host_link_probe(devices, 256 << 20, 5)
+
+    def call(in_ptrs, out_ptrs, count):
+        if world == 1:
+            pipe.tensor_stream_raw(ec.EC_STREAM_RIGHT, Fh.ctypes.data, n, n, in_ptrs, out_ptrs, count, n, n)
+        else:
+            pipe.tensor_stream_raw_multi(devices, ec.EC_STREAM_RIGHT, Fh.ctypes.data, n, n, in_ptrs, out_ptrs,
+                                         count, n, n)
+
+    def check(out_col, gid, what):
+        want = orc.cpu_product(orc.fill_uniform(SEED, gid, (n, n)), Fh)
+        err = orc.rel_frobenius(out_col.reshape(n, n, order="F"), want)
+        if not err <= 1e-12:
+            raise SystemExit(f"bench.py: {what} parity check failed, rel. Frobenius error {err}")
+
+    # ---- pinned host memory (the contract's e2e) ----
+    pin_in, pin_out = ec.PinnedBuffer((elems, total)), ec.PinnedBuffer((elems, total))
+    hin = torch.from_numpy(pin_in.array.reshape(-1, order="F"))
+    block = min(total, 1024)
+    scratch = torch.empty(block * elems, dtype=torch.float64, device=dev)
+    for off in range(0, total, block):                       # tensor element i has matrix_id i + 1
+        nb = min(block, total - off)
+        pipe.fill_uniform(SEED, 1 + off, scratch.data_ptr(), elems, nb)
+        hin[off * elems:(off + nb) * elems].copy_(scratch[: nb * elems])
+    torch.cuda.synchronize()
+    del scratch
+    in_ptrs = (C.c_void_p * total)(*[pin_in.ptr + mbytes * i for i in range(total)])
+    out_ptrs = (C.c_void_p * total)(*[pin_out.ptr + mbytes * i for i in range(total)])
+    pipe.set_stream_config(args.chunk, args.ring, 0)
+    esteps = args.e2e_steps or min(args.steps, 5)
+    for _ in range(2):
+        call(in_ptrs, out_ptrs, total)       # warm-up: engine rings, child pipelines, NCCL communicators
+    l0 = pipe.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(esteps):
+        call(in_ptrs, out_ptrs, total)       # returns with every result in host memory
+    dt = time.perf_counter() - t0
+    launches = pipe.launch_count() - l0
+    for i in (0, total // 3, total - 1):     # first shard, a middle one, the last matrix of the last shard
+        check(pin_out.array[:, i], i + 1, "e2e (pinned)")
+    rate = total * esteps / dt
+    gbs = total * mbytes * esteps / dt / 1e9
+    e2e = {"value": rate, "unit": "matrices/s", "h2d_bytes_per_step": total * mbytes, "d2h_bytes_per_step": total * mbytes,
+           "steps": esteps, "matrices_per_gpu": per_gpu, "matrices_total": total, "ms_per_step": 1e3 * dt / esteps,
+           "host_memory": "pinned (cudaHostAlloc), DMA'd in place",
+           "api": ("ec_tensor_stream_run (CudaPipeline::right_multiply)" if world == 1 else
+                   f"ec_tensor_stream_run_multi over {world} GPUs (CudaPipeline::right_multiply(tensor, A, devices)): one call, "
+                   f"one process, one worker thread + ring per GPU, NCCL broadcast of F inside the timed region"),
+           "tflops": rate * 2.0 * n ** 3 / 1e12, "gpu_launches_per_step": launches / esteps,
+           "link_gbs_each_way": gbs, "link_gbs_each_way_per_gpu": gbs / world,
+           "link_roofline_gbs": {"h2d_only": link["h2d"], "d2h_only": link["d2h"],
+                                 "bidirectional_each_way": link["bidir_each_way"],
+                                 "how": f"plain pinned cudaMemcpyAsync, 256 MiB per copy, on all {world} GPU(s) at once, best of 5, "
+                                        f"measured in this run just before the leg; GB/s summed over the GPUs"},
+           "frac_of_link": gbs / link["bidir_each_way"] if link["bidir_each_way"] else None}
+    if note:
+        e2e["note"] = note
+
+    # ---- pageable host memory (what a std::vector<Eigen::MatrixXd> is; what the reference arm runs from) ----
+    ptotal = min(total, e2e_matrices_per_gpu(args, 1))
+    base = np.empty((elems, ptotal), dtype=np.float64, order="F")
+    np.copyto(base, pin_in.array[:, :ptotal])
+    pin_in.close()
+    pin_out.close()
+    outs = np.zeros((elems, ptotal), dtype=np.float64, order="F")      # touched: no page faults in the timed region
+    ipp = (C.c_void_p * ptotal)(*[base.ctypes.data + mbytes * i for i in range(ptotal)])
+    opp = (C.c_void_p * ptotal)(*[outs.ctypes.data + mbytes * i for i in range(ptotal)])
+    call(ipp, opp, ptotal)
+    psteps = max(2, min(esteps, 3))
+    t0 = time.perf_counter()
+    for _ in range(psteps):
+        call(ipp, opp, ptotal)
+    dt = time.perf_counter() - t0
+    for i in (0, ptotal - 1):
+        check(outs[:, i], i + 1, "e2e (pageable)")
+    prate = ptotal * psteps / dt
+    e2e_pageable = {"value": prate, "unit": "matrices/s", "h2d_bytes_per_step": ptotal * mbytes,
+                    "d2h_bytes_per_step": ptotal * mbytes, "steps": psteps, "matrices_total": ptotal,
+                    "ms_per_step": 1e3 * dt / psteps,
+                    "host_memory": "pageable (numpy heap memory), staged through the engines' pinned rings by worker threads",
+                    "host_gbs_each_way": ptotal * mbytes * psteps / dt / 1e9, "host_threads": len(os.sched_getaffinity(0)),
+                    "what": "the same one call on the memory the reference arm runs from: separates 'API + overlap' "
+                            "(this figure / reference) from 'caller pins its matrices' (e2e / reference)"}
+    pipe.set_stream_config(0, 0, 0)
+    return e2e, e2e_pageable
 
 
 def main():
@@ -309,89 +459,82 @@ def main():
     else:
         err = None
 
-    # ---- e2e: through the C-ABI tensor-stream call with pinned host buffers ----
-    e2e = None
+    # ---- e2e legs: ONE call of the public API (the multi-GPU scheduler inside the library) over
+    # all N GPUs, issued by rank 0 -- what a caller with one std::vector<Eigen::MatrixXd> does.
+    # The other ranks have nothing to do here and wait on a host-side (gloo) barrier.
+    Fh = np.asfortranarray(F.cpu().numpy().reshape(n, n, order="F"))   # the fixed operand as host memory
+    del T, R
+    torch.cuda.empty_cache()
+    host_group = dist.new_group(backend="gloo") if world > 1 else None
+
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=host_group)
+
+    e2e = e2e_pageable = None
     if not args.no_e2e:
-        # per-rank pinned buffers: 2 x 8 GiB at the default size; halve from 4 ranks up (host RAM)
-        ecount = args.e2e_count or (count if world <= 2 else max(64, count // 2))
-        pin_in = pin_out = None
-        while ecount >= 64:
-            try:
-                pin_in = ec.PinnedBuffer((elems, ecount))
-                pin_out = ec.PinnedBuffer((elems, ecount))
-                break
-            except ec.EigenCudaError:
-                if pin_in is not None:
-                    pin_in.close()
-                pin_in = None
-                ecount //= 2
-        if pin_in is not None:
-            hin = torch.from_numpy(pin_in.array.reshape(-1, order="F"))
-            hin.copy_(T[: ecount * elems])          # inputs now live in pinned HOST memory
-            torch.cuda.synchronize()
-            in_ptrs = (C.c_void_p * ecount)(*[pin_in.ptr + 8 * elems * i for i in range(ecount)])
-            out_ptrs = (C.c_void_p * ecount)(*[pin_out.ptr + 8 * elems * i for i in range(ecount)])
+        torch.cuda.synchronize()
+        host_barrier()
+        if rank == 0:
+            e2e, e2e_pageable = e2e_legs(args, ec, orc, pipe, torch, dev, world, Fh)
+        host_barrier()
 
-            def step_e2e():
-                pipe.tensor_stream_raw(ec.EC_STREAM_RIGHT, F.data_ptr(), n, n, in_ptrs, out_ptrs, ecount, n, n)
-
-            pipe.set_stream_config(args.chunk, args.ring, 0)
-            esteps = args.e2e_steps or min(args.steps, 5)
-            step_e2e()                                # warm-up (allocates the engine's ring)
-            torch.cuda.synchronize()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(esteps):
-                step_e2e()                            # returns with all results in host memory
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            barrier()
-            dt = max_over_ranks(dt)
-            if rank == 0:
-                got = pin_out.array[:, ecount // 3].reshape(n, n, order="F")
-                want = orc.cpu_product(orc.fill_uniform(SEED, first_id + ecount // 3, (n, n)),
-                                       orc.fill_uniform(SEED, 0, (n, n)))
-                e_err = orc.rel_frobenius(got, want)
-                if not e_err <= 1e-12:
-                    raise SystemExit(f"bench.py: e2e parity check failed, rel. Frobenius error {e_err}")
-            e_val = world * ecount * esteps / dt
-            e2e = {"value": e_val, "unit": "matrices/s",
-                   "h2d_bytes_per_step": ecount * elems * 8, "d2h_bytes_per_step": ecount * elems * 8,
-                   "steps": esteps, "matrices_per_gpu": ecount, "ms_per_step": 1e3 * dt / esteps,
-                   "host_memory": "pinned (cudaHostAlloc), DMA'd in place",
-                   "tflops": e_val * flops_per_matrix / 1e12,
-                   "link_gbs_each_way_per_gpu": ecount * elems * 8 * esteps / dt / 1e9}
-            pin_in.close()
-            pin_out.close()
-
-    # ---- configs[1]: square DGEMM sweep on one GPU (rank 0, N=1) ----
+    # ---- configs[1]: square DGEMM sweep on one GPU (rank 0, N=1), cuBLAS beside it at every n ----
+    # cuBLAS = torch.mm on float64 CUDA tensors (cublasDgemm, the reference's arithmetic,
+    # src/cudapipeline.cc:29-31), timed exactly like ours: best single call between two events on
+    # the launching stream, and the average of a back-to-back run.
     sweep = None
     if world == 1 and not args.no_sweep:
         sweep = []
-        del T, R
         torch.cuda.empty_cache()
-        for nn in (256, 512, 1024, 2048, 4096, 8192, 16384):
-            A = torch.empty(nn * nn, dtype=torch.float64, device=dev)
-            B = torch.empty(nn * nn, dtype=torch.float64, device=dev)
-            Cm = torch.empty(nn * nn, dtype=torch.float64, device=dev)
-            pipe.fill_uniform(SEED, 0, A.data_ptr(), nn * nn, 1)
-            pipe.fill_uniform(SEED, 1, B.data_ptr(), nn * nn, 1)
-            reps = 2 if nn >= 16384 else 3 if nn >= 8192 else 10
-            for _ in range(1 if nn >= 16384 else 3):
-                pipe.dgemm(0, 0, nn, nn, nn, 1.0, A.data_ptr(), nn, B.data_ptr(), nn, 0.0, Cm.data_ptr(), nn)
+
+        def time_calls(fn, reps, b2b):
             best = float("inf")
             for _ in range(reps):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream)
-                pipe.dgemm(0, 0, nn, nn, nn, 1.0, A.data_ptr(), nn, B.data_ptr(), nn, 0.0, Cm.data_ptr(), nn)
+                fn()
                 b.record(stream)
                 b.synchronize()
                 best = min(best, a.elapsed_time(b))
-            tf = 2.0 * nn ** 3 / (best * 1e-3) / 1e12
-            sweep.append({"n": nn, "ms": best, "tflops": tf, "frac_of_datasheet_fp64": tf / FP64_DATASHEET_TFLOPS,
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(b2b):
+                fn()
+            b.record(stream)
+            b.synchronize()
+            return best, a.elapsed_time(b) / b2b
+
+        for nn in (256, 512, 1024, 2048, 4096, 8192, 16384):
+            A = torch.empty((nn, nn), dtype=torch.float64, device=dev)
+            B = torch.empty((nn, nn), dtype=torch.float64, device=dev)
+            Cm = torch.empty((nn, nn), dtype=torch.float64, device=dev)
+            Cb = torch.empty((nn, nn), dtype=torch.float64, device=dev)
+            pipe.fill_uniform(SEED, 0, A.data_ptr(), nn * nn, 1)
+            pipe.fill_uniform(SEED, 1, B.data_ptr(), nn * nn, 1)
+            reps = 2 if nn >= 16384 else 3 if nn >= 8192 else 10
+            b2b = 2 if nn >= 16384 else 3 if nn >= 8192 else 50 if nn <= 1024 else 10
+            ours = lambda: pipe.dgemm(0, 0, nn, nn, nn, 1.0, A.data_ptr(), nn, B.data_ptr(), nn, 0.0, Cm.data_ptr(), nn)
+            # row-major view: Cb^T = B^T A^T is the same column-major product C = A * B
+            cublas = lambda: torch.mm(B, A, out=Cb)
+            for _ in range(1 if nn >= 16384 else 3):
+                ours()
+                cublas()
+            best, avg = time_calls(ours, reps, b2b)
+            cbest, cavg = time_calls(cublas, reps, b2b)
+            same = float((Cm - Cb).norm() / Cb.norm())
+            fl = 2.0 * nn ** 3
+            sweep.append({"n": nn, "ms": best, "tflops": fl / best / 1e9, "tflops_back_to_back": fl / avg / 1e9,
+                          "cublas_tflops": fl / cbest / 1e9, "cublas_tflops_back_to_back": fl / cavg / 1e9,
+                          "vs_cublas": cbest / best, "vs_cublas_back_to_back": cavg / avg,
+                          "rel_frobenius_vs_cublas": same,
+                          "frac_of_datasheet_fp64": fl / best / 1e9 / FP64_DATASHEET_TFLOPS,
                           "hbm_gbs": 24.0 * nn * nn / best / 1e6,   # algorithmic: read A and B, write C
                           "kernel": pipe.last_kernel()})
-            del A, B, Cm
+            if not same <= 1e-12:
+                raise SystemExit(f"bench.py: n={nn} differs from cuBLAS by {same} (relative Frobenius)")
+            del A, B, Cm, Cb
+        torch.cuda.empty_cache()
 
     # ---- extras (rank 0, N=1): configs[3] and the pageable-host variant of the e2e leg ----
     extras = None
@@ -520,25 +663,11 @@ def main():
         pipe.set_backend(ec.EC_BACKEND_FP64_DMMA)
         extras["ozaki_i8"] = oz
         torch.cuda.empty_cache()
-        # the main workload from PAGEABLE host memory (what a std::vector<Eigen::MatrixXd> is):
-        # staged through the engine's pinned ring by worker threads
-        cp_ = 1024
-        Fh = np.asfortranarray(F.cpu().numpy().reshape(n, n, order="F"))
+        cp_ = 256
         base = np.empty((elems, cp_), dtype=np.float64, order="F")
         Tsrc = torch.empty(cp_ * elems, dtype=torch.float64, device=dev)
         pipe.fill_uniform(SEED, 1, Tsrc.data_ptr(), elems, cp_)
         torch.from_numpy(base.reshape(-1, order="F")).copy_(Tsrc)
-        outs = np.empty((elems, cp_), dtype=np.float64, order="F")
-        ipp = (C.c_void_p * cp_)(*[base.ctypes.data + 8 * elems * i for i in range(cp_)])
-        opp = (C.c_void_p * cp_)(*[outs.ctypes.data + 8 * elems * i for i in range(cp_)])
-        pipe.tensor_stream_raw(ec.EC_STREAM_RIGHT, Fh.ctypes.data, n, n, ipp, opp, cp_, n, n)
-        t0 = time.perf_counter()
-        for _ in range(2):
-            pipe.tensor_stream_raw(ec.EC_STREAM_RIGHT, Fh.ctypes.data, n, n, ipp, opp, cp_, n, n)
-        dt = (time.perf_counter() - t0) / 2
-        extras["e2e_pageable"] = {"matrices": cp_, "n": n, "ms_per_step": 1e3 * dt, "matrices_per_s": cp_ / dt,
-                                  "host_gbs_each_way": cp_ * elems * 8 / dt / 1e9,
-                                  "host_memory": "pageable, staged through pinned ring by worker threads"}
         # the reference's own loop shape through the compat API (copy_to_gpu -> gemm -> convert,
         # pageable memory, one stream): what a caller gets with NO source change at all
         cl = 256
@@ -560,7 +689,7 @@ def main():
         extras["compat_loop_pageable"] = {"matrices": cl, "n": n, "matrices_per_s": rates[len(rates) // 2],
                                           "matrices_per_s_min_max": [rates[0], rates[-1]], "repeats": len(rates),
                                           "what": "README.md:62-66 loop through CudaMatrix/CudaPipeline of this repo, unchanged caller code"}
-        del Tsrc, base, outs, ts_h
+        del Tsrc, base, ts_h
         # the same three ways of driving the library from C++ caller code (examples/readme_loop.cc,
         # compiled against include/*.hpp by __graft_entry__.build())
         exe = os.path.join(ROOT, "tools", "bin", "readme_loop")
@@ -575,8 +704,9 @@ def main():
                 extras["cpp_readme_loop"] = {"error": repr(exc)[:300]}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu:
         cpu = cpu_baseline(n, args.cpu_seconds)
+    host_barrier()
 
     if rank == 0:
         traffic = None
@@ -594,6 +724,12 @@ def main():
             hbm_frac = (count * 2 * elems * 8 + elems * 8) / (kernel_ms * 1e-3) / 1e9 / mp["hbm_gbs"]
         except Exception:
             pass
+        sm_mhz = (clocks or {}).get("sm_mhz")
+        cublas_8192 = None
+        if sweep:
+            cublas_8192 = next((r["cublas_tflops"] for r in sweep if r["n"] == 8192), None)
+        if cublas_8192 is None and peaks:
+            cublas_8192 = next((r["tflops"] for r in peaks.get("cublas_dgemm", []) if r["n"] == 8192), None)
         roofline = {"bound": "tensor", "achieved": achieved_tflops, "peak": FP64_DATASHEET_TFLOPS,
                     "unit": "TFLOP/s", "frac": achieved_tflops / FP64_DATASHEET_TFLOPS, "traffic": traffic,
                     "kernel": "dgemm_tma_dmma_kernel<CfgL,NN> (FP64 DMMA, mma.sync.m8n8k4), variant " + kernel_name,
@@ -603,7 +739,18 @@ def main():
                     "hbm_gbs_achieved": (count * 2 * elems * 8 + elems * 8) / (kernel_ms * 1e-3) / 1e9,
                     "hbm_frac_of_measured_peak": hbm_frac,
                     "peak_source": "datasheet-derived FP64 peak 148 SM x 128 flop/clk x 1.965 GHz "
-                                   "(MEASURED_PEAKS.json has no FP64 figure; of fallback/datasheet)"}
+                                   "(MEASURED_PEAKS.json has no FP64 figure; of fallback/datasheet)",
+                    # the three candidate FP64 peaks side by side
+                    "peaks_tflops": {"datasheet": FP64_DATASHEET_TFLOPS,
+                                     "clock_scaled": 148 * 128 * sm_mhz * 1e6 / 1e12 if sm_mhz else None,
+                                     "clock_scaled_at_sm_mhz": sm_mhz,
+                                     "measured_cublas_dgemm_n8192": cublas_8192,
+                                     "measured_dmma_issue": peaks.get("dmma_peak_tflops") if peaks else None},
+                    "frac_of": {"datasheet": achieved_tflops / FP64_DATASHEET_TFLOPS,
+                                "clock_scaled": achieved_tflops / (148 * 128 * sm_mhz * 1e6 / 1e12) if sm_mhz else None,
+                                "measured_cublas_dgemm_n8192": achieved_tflops / cublas_8192 if cublas_8192 else None,
+                                "measured_dmma_issue": achieved_tflops / peaks["dmma_peak_tflops"]
+                                if peaks and peaks.get("dmma_peak_tflops") else None}}
         if peaks:
             roofline["measured_dmma_issue_peak_tflops"] = peaks.get("dmma_peak_tflops")
             roofline["measured_dmma_sustained_tflops"] = peaks.get("dmma_sustained_tflops")
@@ -613,14 +760,10 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"tensor_stream_right (BASELINE.json configs[2]): {count} matrices "
-                                       f"T_i({n}x{n}) per GPU, R_i = T_i * F({n}x{n}), FP64 column-major",
-                           "matrices_per_gpu": count, "n": n, "kind": "right",
-                           "parallelism": f"tensor sharded over {world} GPU(s), fixed operand broadcast once",
-                           "l2": f"inputs {count * elems * 8 / 2**30:.1f} GiB per step per GPU > 126 MB L2; no flush needed",
-                           "generator": "splitmix64 counter-based, seed 20200210"},
+                "config": make_config(args, world),
                 "tflops": value * flops_per_matrix / 1e12,
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "e2e": e2e, "e2e_pageable": e2e_pageable, "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": roofline,
                 "cpu_baseline": cpu, "dgemm": sweep, "extras": extras, "peaks": peaks,
                 "parity_rel_frobenius": err}
         print(json.dumps(line), flush=True)

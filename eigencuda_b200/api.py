@@ -143,11 +143,15 @@ class CudaPipeline:
                                            int(A), lda, sa, int(B), ldb, sb, float(beta), int(Cp),
                                            ldc, sc, batch))
 
-    def tensor_stream(self, kind, F, tensor, results=None):
+    def tensor_stream(self, kind, F, tensor, results=None, devices=None):
         """The reference's streaming loop (README.md:62-66, src/tests/test_dot.cc:81-85) as one
         overlapped job.  `tensor` is a sequence of equally-shaped matrices (a Python list of
         Fortran-ordered float64 arrays == std::vector<Eigen::MatrixXd>), `F` the fixed matrix.
-        Returns the list of results; `results` may supply preallocated outputs."""
+        Returns the list of results; `results` may supply preallocated outputs (float64,
+        Fortran-contiguous, writeable, of the result shape -- anything else raises ValueError
+        instead of being written through).  `devices`: None = this pipeline's device; a list of
+        device indices (or "all") = the multi-GPU scheduler (ec_tensor_stream_run_multi): the
+        tensor is sharded into contiguous ranges, F broadcast once with NCCL."""
         F = _as_eigen(F)
         ts = [_as_eigen(t) for t in tensor]
         n = len(ts)
@@ -159,24 +163,50 @@ class CudaPipeline:
         r_shape = result_shape(kind, F.shape, (t_rows, t_cols))
         if results is None:
             results = [np.empty(r_shape, dtype=np.float64, order="F") for _ in range(n)]
+        else:
+            results = list(results)     # keeps the arrays alive for the duration of the call
+            if len(results) != n:
+                raise ValueError(f"results has {len(results)} elements, tensor has {n}")
+            for i, r in enumerate(results):
+                if not isinstance(r, np.ndarray) or r.dtype != np.float64:
+                    raise ValueError(f"results[{i}] must be a float64 numpy array")
+                if r.shape != tuple(r_shape):
+                    raise ValueError(f"results[{i}] has shape {r.shape}, the product has shape {tuple(r_shape)}")
+                if not r.flags.f_contiguous:
+                    raise ValueError(f"results[{i}] must be Fortran-contiguous (column-major, ld = rows)")
+                if not r.flags.writeable:
+                    raise ValueError(f"results[{i}] is read-only")
         in_ptrs = (C.c_void_p * n)(*[t.ctypes.data for t in ts])
         out_ptrs = (C.c_void_p * n)(*[r.ctypes.data for r in results])
-        check(lib.ec_tensor_stream_run(self._h, int(kind), F.ctypes.data, F.shape[0], F.shape[1],
-                                       in_ptrs, out_ptrs, n, t_rows, t_cols))
+        if devices is None:
+            check(lib.ec_tensor_stream_run(self._h, int(kind), F.ctypes.data, F.shape[0], F.shape[1],
+                                           in_ptrs, out_ptrs, n, t_rows, t_cols))
+        else:
+            dev_arr, ndev = _device_list(devices)
+            check(lib.ec_tensor_stream_run_multi(self._h, dev_arr, ndev, int(kind), F.ctypes.data, F.shape[0],
+                                                 F.shape[1], in_ptrs, out_ptrs, n, t_rows, t_cols))
         return results
 
-    def right_multiply(self, tensor, F):
+    def right_multiply(self, tensor, F, devices=None):
         """results[i] = tensor[i] * F -- the order the reference's README/test use."""
-        return self.tensor_stream(_lib.EC_STREAM_RIGHT, F, tensor)
+        return self.tensor_stream(_lib.EC_STREAM_RIGHT, F, tensor, devices=devices)
 
-    def left_multiply(self, F, tensor, transpose=False):
+    def left_multiply(self, F, tensor, transpose=False, devices=None):
         """results[i] = F * tensor[i]  (or F^T * tensor[i])."""
-        return self.tensor_stream(_lib.EC_STREAM_LEFT_T if transpose else _lib.EC_STREAM_LEFT, F, tensor)
+        return self.tensor_stream(_lib.EC_STREAM_LEFT_T if transpose else _lib.EC_STREAM_LEFT, F, tensor,
+                                  devices=devices)
 
-    def basis_transform(self, F, tensor):
+    def basis_transform(self, F, tensor, devices=None):
         """results[i] = F^T * tensor[i] * F  (BASELINE.json config 4; two products, the
         intermediate never leaves the device)."""
-        return self.tensor_stream(_lib.EC_STREAM_BASIS, F, tensor)
+        return self.tensor_stream(_lib.EC_STREAM_BASIS, F, tensor, devices=devices)
+
+    def tensor_stream_raw_multi(self, devices, kind, F_ptr, f_rows, f_cols, in_ptrs, out_ptrs, count,
+                                t_rows, t_cols):
+        """Pointer-level form of the multi-GPU job (ec_tensor_stream_run_multi)."""
+        dev_arr, ndev = _device_list(devices)
+        check(lib.ec_tensor_stream_run_multi(self._h, dev_arr, ndev, int(kind), int(F_ptr), f_rows, f_cols,
+                                             in_ptrs, out_ptrs, count, t_rows, t_cols))
 
     def tensor_stream_raw(self, kind, F_ptr, f_rows, f_cols, in_ptrs, out_ptrs, count, t_rows, t_cols):
         """Pointer-level form: `F_ptr` may be a host or a device address (the latter after the
@@ -231,6 +261,34 @@ class CudaPipeline:
             self.close()
         except Exception:
             pass
+
+
+def _device_list(devices):
+    """("all" | iterable of device indices) -> (ctypes int array or None, ndev); ndev 0 = every device."""
+    if isinstance(devices, str):
+        if devices != "all":
+            raise ValueError('devices must be a list of device indices or "all"')
+        return None, 0
+    devs = [int(d) for d in devices]
+    if not devs:
+        raise ValueError("empty device list")
+    return (C.c_int * len(devs))(*devs), len(devs)
+
+
+def plan_shard(count, ndev, idx):
+    """[lo, hi) of a `count`-element tensor that device number `idx` of `ndev` takes in the multi-GPU job."""
+    lo, hi = C.c_int64(), C.c_int64()
+    check(lib.ec_plan_shard(int(count), int(ndev), int(idx), C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
+def host_link_probe(devices="all", nbytes=256 << 20, reps=5):
+    """Measured host-link ceiling in GB/s summed over `devices`: plain pinned cudaMemcpyAsync on all
+    of them at once (ec_host_link_probe).  Returns {"h2d", "d2h", "bidir_each_way"}."""
+    dev_arr, ndev = _device_list(devices)
+    out = (C.c_double * 3)()
+    check(lib.ec_host_link_probe(dev_arr, ndev, int(nbytes), int(reps), out))
+    return {"h2d": out[0], "d2h": out[1], "bidir_each_way": out[2]}
 
 
 def plan_dgemm(m, n, k, batch=1, sm_count=148):

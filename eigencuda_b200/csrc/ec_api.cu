@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -34,6 +35,8 @@
 #include "ozaki_dispatch.inl"   // int8 emulation backend: split + GEMM launches
 #include "dgemm_dispatch.inl"   // validation, corner cases, backend / kernel choice
 #include "stream_engine.inl"    // overlapped tensor-stream engine
+#include "stream_run.inl"       // one tensor-stream job on one device (feeder + drainer)
+#include "multi_gpu.inl"        // the same job sharded over several devices of one box (NCCL broadcast)
 
 // ------------------------------------------------------------------------------------------
 // C ABI
@@ -129,6 +132,11 @@ int ec_pipeline_destroy(ec_pipeline *p) {
     auto it = g_registry.find((void *)p->stream);
     if (it != g_registry.end() && it->second == p) g_registry.erase(it);
   }
+  if (p->multi) {
+    p->multi->destroy();
+    delete p->multi;
+    p->multi = nullptr;
+  }
   if (p->engine) {
     p->engine->destroy();
     delete p->engine;
@@ -136,6 +144,7 @@ int ec_pipeline_destroy(ec_pipeline *p) {
   p->staging.destroy();
   delete p->compat_pool;
   p->compat_pool = nullptr;
+  if (p->ev_order) cudaEventDestroy(p->ev_order);
   if (p->sk_workspace) cudaFree(p->sk_workspace);
   if (p->sk_flags) cudaFree(p->sk_flags);
   if (p->oz_planes_a) cudaFree(p->oz_planes_a);
@@ -322,14 +331,23 @@ int ec_matrix_upload(ec_matrix *m, const double *host, int64_t count) {
   const size_t bytes = (size_t)count * sizeof(double);
   ec_pipeline *p = pipeline_of_stream(m->stream);
   if (p && !is_pinned_host(host)) {
-    int slot = -1;
-    int rc = p->staging.acquire(bytes, &slot);
-    if (rc) return rc;
-    compat_copy(p, p->staging.buf[slot], host, bytes);
-    cudaError_t e =
-        cudaMemcpyAsync(m->data, p->staging.buf[slot], bytes, cudaMemcpyHostToDevice, m->stream);
-    if (e != cudaSuccess) return fail(EC_ERR_COPY, "Error copy arrays to device: %s", cudaGetErrorString(e));
-    return p->staging.release_after(slot, m->stream);
+    // Whole-matrix staging up to 8 MiB (one DMA: the bench shapes); anything larger goes in 4 MiB
+    // pieces over the rotating slots, so that the host copy of piece i+1 runs under the DMA of
+    // piece i and a 2 GiB matrix pins 16 MiB of staging, not 2 GiB per slot.
+    const size_t PIECE = bytes <= ((size_t)8 << 20) ? bytes : ((size_t)4 << 20);
+    for (size_t off = 0; off < bytes; off += PIECE) {
+      const size_t len = std::min(PIECE, bytes - off);
+      int slot = -1;
+      int rc = p->staging.acquire(len, &slot);
+      if (rc) return rc;
+      compat_copy(p, p->staging.buf[slot], (const char *)host + off, len);
+      cudaError_t e = cudaMemcpyAsync((char *)m->data + off, p->staging.buf[slot], len,
+                                      cudaMemcpyHostToDevice, m->stream);
+      if (e != cudaSuccess) return fail(EC_ERR_COPY, "Error copy arrays to device: %s", cudaGetErrorString(e));
+      rc = p->staging.release_after(slot, m->stream);
+      if (rc) return rc;
+    }
+    return EC_OK;
   }
   cudaError_t e = cudaMemcpyAsync(m->data, host, bytes, cudaMemcpyHostToDevice, m->stream);
   if (e != cudaSuccess) return fail(EC_ERR_COPY, "Error copy arrays to device: %s", cudaGetErrorString(e));
@@ -407,16 +425,22 @@ double *ec_matrix_data(const ec_matrix *m) { return m ? m->data : nullptr; }
 int ec_gemm(ec_pipeline *p, const ec_matrix *A, const ec_matrix *B, ec_matrix *C) {
   if (!p || !A || !B || !C) return fail(EC_ERR_ARG, "null handle");
   if (A->cols != B->rows) return fail(EC_ERR_SHAPE, "Shape mismatch in Cublas gemm");
+  DeviceGuard guard(p->device);
   // Operands created on another stream than the pipeline's: the reference is ordered by the
-  // legacy NULL stream in that case; here the dependency is made explicit.
+  // legacy NULL stream in that case; here the dependency is made explicit.  One event per
+  // pipeline, created on its device and kept: nothing to leak on an error path.
   const ec_matrix *ops[3] = {A, B, C};
-  for (const ec_matrix *m : ops) {
-    if (m->stream != p->stream) {
-      cudaEvent_t ev;
-      EC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      EC_CUDA(cudaEventRecord(ev, m->stream));
-      EC_CUDA(cudaStreamWaitEvent(p->stream, ev, 0));
-      EC_CUDA(cudaEventDestroy(ev));
+  bool foreign = false;
+  for (const ec_matrix *m : ops) foreign = foreign || m->stream != p->stream;
+  if (foreign) {
+    for (const ec_matrix *m : ops)
+      if (m->device != p->device)
+        return fail(EC_ERR_ARG, "gemm: operand lives on device %d, the pipeline on device %d", m->device, p->device);
+    if (!p->ev_order) EC_CUDA(cudaEventCreateWithFlags(&p->ev_order, cudaEventDisableTiming));
+    for (const ec_matrix *m : ops) {
+      if (m->stream == p->stream) continue;
+      EC_CUDA(cudaEventRecord(p->ev_order, m->stream));
+      EC_CUDA(cudaStreamWaitEvent(p->stream, p->ev_order, 0));
     }
   }
   int rc = dgemm_dispatch(p, EC_OP_N, EC_OP_N, A->rows, B->cols, A->cols, 1.0, A->data, A->rows, 0,
@@ -424,16 +448,11 @@ int ec_gemm(ec_pipeline *p, const ec_matrix *A, const ec_matrix *B, ec_matrix *C
   if (rc) return rc;
   // ... and in the other direction: whatever the operands' own streams do next -- read the result,
   // overwrite an input, release a pooled buffer in stream order -- comes after this product.
-  cudaEvent_t done = nullptr;
-  for (const ec_matrix *m : ops) {
-    if (m->stream == p->stream) continue;
-    if (!done) {
-      EC_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-      EC_CUDA(cudaEventRecord(done, p->stream));
-    }
-    EC_CUDA(cudaStreamWaitEvent(m->stream, done, 0));
+  if (foreign) {
+    EC_CUDA(cudaEventRecord(p->ev_order, p->stream));
+    for (const ec_matrix *m : ops)
+      if (m->stream != p->stream) EC_CUDA(cudaStreamWaitEvent(m->stream, p->ev_order, 0));
   }
-  if (done) EC_CUDA(cudaEventDestroy(done));
   return EC_OK;
 }
 
@@ -486,207 +505,25 @@ int ec_tensor_stream_run_device(ec_pipeline *p, int kind, const double *F_dev, i
 int ec_tensor_stream_run(ec_pipeline *p, int kind, const double *F, int64_t f_rows, int64_t f_cols,
                          const double *const *tensor, double *const *results, int64_t count,
                          int64_t t_rows, int64_t t_cols) {
-  if (!p) return fail(EC_ERR_ARG, "null pipeline");
-  if (count < 0 || f_rows < 0 || f_cols < 0 || t_rows < 0 || t_cols < 0)
-    return fail(EC_ERR_ARG, "negative size");
-  StreamShape sh;
-  int rc = stream_shape(kind, f_rows, f_cols, t_rows, t_cols, &sh);  // before any device work
-  if (rc) return rc;
-  if (count == 0) return EC_OK;
-  if (!F || !tensor || !results) return fail(EC_ERR_ARG, "null pointer");
-  const int64_t t_sz = t_rows * t_cols, r_sz = sh.r_rows * sh.r_cols, f_sz = f_rows * f_cols;
-  if (t_sz == 0 || r_sz == 0 || f_sz == 0) {
-    // degenerate: products with an empty inner dimension are all-zero
-    for (int64_t i = 0; i < count; ++i)
-      if (r_sz) std::memset(results[i], 0, (size_t)r_sz * 8);
-    return EC_OK;
-  }
-  DeviceGuard guard(p->device);
-  TraceRange trace("ec_tensor_stream_run");
+  return tensor_stream_run_impl(p, kind, F, f_rows, f_cols, tensor, results, count, t_rows, t_cols);
+}
 
-  // ---- plan ----
-  bool in_pinned = true, out_pinned = true;
-  // One attribute query per run of adjacent matrices (first and last element of the run), not
-  // per matrix: a contiguous tensor costs two queries.
-  auto all_pinned = [&](const double *const *ptrs, int64_t elems) {
-    int64_t i = 0;
-    while (i < count) {
-      int64_t j = i + 1;
-      while (j < count && ptrs[j] == ptrs[j - 1] + elems) ++j;
-      if (!is_pinned_host(ptrs[i]) || !is_pinned_host(ptrs[j - 1] + elems - 1)) return false;
-      i = j;
-    }
-    return true;
-  };
-  in_pinned = all_pinned(tensor, t_sz);
-  out_pinned = all_pinned((const double *const *)results, r_sz);
-  const bool staged_in = !in_pinned, staged_out = !out_pinned;
-  int64_t chunk = p->cfg_chunk;
-  if (chunk <= 0) chunk = std::max<int64_t>(1, ((int64_t)32 << 20) / (8 * std::max(t_sz, r_sz)));
-  chunk = std::min(chunk, count);
-  const int ring = p->cfg_ring > 0 ? p->cfg_ring : 3;
-  int threads = p->cfg_threads;
-  if (threads <= 0) threads = std::max(2u, std::min(16u, std::thread::hardware_concurrency()));
-  if (!p->engine) {
-    p->engine = new StreamEngine();
-    p->engine->p = p;
-  }
-  StreamEngine &E = *p->engine;
-  const bool f_on_device = is_device_ptr(F);
-  const size_t tmp_b = kind == EC_STREAM_BASIS ? (size_t)(chunk * f_cols * t_cols * 8) : 0;
-  rc = E.ensure(ring, (size_t)(chunk * t_sz * 8), (size_t)(chunk * r_sz * 8), tmp_b,
-                f_on_device ? 0 : (size_t)(f_sz * 8), staged_in, staged_out, threads);
-  if (rc) return rc;
+int ec_tensor_stream_run_multi(ec_pipeline *p, const int *devices, int ndev, int kind, const double *F,
+                               int64_t f_rows, int64_t f_cols, const double *const *tensor,
+                               double *const *results, int64_t count, int64_t t_rows, int64_t t_cols) {
+  return tensor_stream_run_multi_impl(p, devices, ndev, kind, F, f_rows, f_cols, tensor, results, count,
+                                      t_rows, t_cols);
+}
 
-  // Order the engine's streams after whatever the caller queued on the pipeline stream.
-  EC_CUDA(cudaEventRecord(E.ev_fixed, p->stream));
-  EC_CUDA(cudaStreamWaitEvent(E.s_h2d, E.ev_fixed, 0));
-  EC_CUDA(cudaStreamWaitEvent(E.s_cmp, E.ev_fixed, 0));
-
-  // ---- fixed operand: uploaded once (or used in place when already on the device, e.g. after
-  // the multi-GPU broadcast) ----
-  const double *dF = F;
-  if (!f_on_device) {
-    int slot = -1;
-    if (is_pinned_host(F)) {
-      EC_CUDA(cudaMemcpyAsync(E.d_fixed, F, (size_t)f_sz * 8, cudaMemcpyHostToDevice, E.s_h2d));
-    } else {
-      rc = p->staging.acquire((size_t)f_sz * 8, &slot);
-      if (rc) return rc;
-      std::memcpy(p->staging.buf[slot], F, (size_t)f_sz * 8);
-      EC_CUDA(cudaMemcpyAsync(E.d_fixed, p->staging.buf[slot], (size_t)f_sz * 8,
-                              cudaMemcpyHostToDevice, E.s_h2d));
-      rc = p->staging.release_after(slot, E.s_h2d);
-      if (rc) return rc;
-    }
-    dF = E.d_fixed;
-  }
-  EC_CUDA(cudaEventRecord(E.ev_fixed, E.s_h2d));
-  EC_CUDA(cudaStreamWaitEvent(E.s_cmp, E.ev_fixed, 0));
-
-  const int64_t nchunks = (count + chunk - 1) / chunk;
-
-  // ---- drainer (pageable results only) ----
-  std::mutex mu;
-  std::condition_variable cv;
-  int64_t enqueued = 0, drained = 0;  // chunks whose D2H is enqueued / whose results are delivered
-  bool abort_flag = false;
-  std::atomic<int> drain_rc{EC_OK};
-  std::thread drainer;
-  if (staged_out) {
-    drainer = std::thread([&] {
-      cudaSetDevice(p->device);
-      for (int64_t c = 0; c < nchunks; ++c) {
-        {
-          std::unique_lock<std::mutex> lk(mu);
-          cv.wait(lk, [&] { return enqueued > c || abort_flag; });
-          if (abort_flag) return;
-        }
-        const int s = (int)(c % ring);
-        if (cudaEventSynchronize(E.ev_d2h[s]) != cudaSuccess) {
-          drain_rc = EC_ERR_CUDA;
-        } else {
-          const int64_t i0 = c * chunk, nb = std::min(chunk, count - i0);
-          TraceRange trace_chunk("deliver chunk (pinned -> caller)");
-          const char *src = (const char *)E.pin_out[s];
-          // split every matrix into a few pieces so the pool stays busy even for small chunks
-          const int pieces = std::max<int>(1, (int)std::min<int64_t>(8, (r_sz * 8) >> 18));
-          E.pool_out->parallel_for(nb * pieces, [&](int64_t t) {
-            const int64_t i = t / pieces, q = t % pieces;
-            const size_t lo = (size_t)(r_sz * 8) * q / pieces, hi = (size_t)(r_sz * 8) * (q + 1) / pieces;
-            // result matrices are often freshly allocated: map the piece in one call, not per page
-            ec_host::prefault_for_write((char *)results[i0 + i] + lo, hi - lo);
-            staging_copy((char *)results[i0 + i] + lo, src + (size_t)i * r_sz * 8 + lo, hi - lo);
-          });
-        }
-        {
-          std::lock_guard<std::mutex> lk(mu);
-          drained = c + 1;
-        }
-        cv.notify_all();
-      }
-    });
-  }
-
-  // ---- feeder (this thread) ----
-  auto feeder = [&]() -> int {
-    for (int64_t c = 0; c < nchunks; ++c) {
-      const int s = (int)(c % ring);
-      const int64_t i0 = c * chunk, nb = std::min(chunk, count - i0);
-      // H2D
-      if (staged_in) {
-        if (c >= ring) EC_CUDA(cudaEventSynchronize(E.ev_h2d[s]));  // pinned_in[s] consumed
-        TraceRange trace_chunk("stage chunk (caller -> pinned)");
-        char *dst = (char *)E.pin_in[s];
-        const int pieces = std::max<int>(1, (int)std::min<int64_t>(8, (t_sz * 8) >> 18));
-        E.pool_in->parallel_for(nb * pieces, [&](int64_t t) {
-          const int64_t i = t / pieces, q = t % pieces;
-          const size_t lo = (size_t)(t_sz * 8) * q / pieces, hi = (size_t)(t_sz * 8) * (q + 1) / pieces;
-          staging_copy(dst + (size_t)i * t_sz * 8 + lo, (const char *)tensor[i0 + i] + lo, hi - lo);
-        });
-      }
-      if (c >= ring) EC_CUDA(cudaStreamWaitEvent(E.s_h2d, E.ev_cmp[s], 0));  // d_in[s] consumed
-      if (staged_in)
-        EC_CUDA(cudaMemcpyAsync(E.d_in[s], E.pin_in[s], (size_t)(nb * t_sz * 8),
-                                cudaMemcpyHostToDevice, E.s_h2d));
-      else if ((rc = dma_chunk(true, E.d_in[s], tensor, i0, nb, t_sz, E.s_h2d)))
-        return rc;
-      EC_CUDA(cudaEventRecord(E.ev_h2d[s], E.s_h2d));
-      // compute (on the engine's compute stream: temporarily retarget the pipeline)
-      EC_CUDA(cudaStreamWaitEvent(E.s_cmp, E.ev_h2d[s], 0));
-      if (c >= ring) EC_CUDA(cudaStreamWaitEvent(E.s_cmp, E.ev_d2h[s], 0));  // d_out[s] drained
-      {
-        StreamScope scope(p, E.s_cmp);
-        rc = stream_compute(p, kind, dF, f_rows, f_cols, E.d_in[s], E.d_out[s],
-                            kind == EC_STREAM_BASIS ? E.d_tmp[s] : nullptr, nb, t_rows, t_cols, sh);
-      }
-      if (rc) return rc;
-      EC_CUDA(cudaEventRecord(E.ev_cmp[s], E.s_cmp));
-      // D2H
-      EC_CUDA(cudaStreamWaitEvent(E.s_d2h, E.ev_cmp[s], 0));
-      if (staged_out) {
-        if (c >= ring) {  // pin_out[s] must have been delivered to the caller
-          std::unique_lock<std::mutex> lk(mu);
-          cv.wait(lk, [&] { return drained >= c - ring + 1 || drain_rc != EC_OK; });
-        }
-        EC_CUDA(cudaMemcpyAsync(E.pin_out[s], E.d_out[s], (size_t)(nb * r_sz * 8),
-                                cudaMemcpyDeviceToHost, E.s_d2h));
-      } else if ((rc = dma_chunk(false, E.d_out[s], (const double *const *)results, i0, nb, r_sz,
-                                 E.s_d2h))) {
-        return rc;
-      }
-      EC_CUDA(cudaEventRecord(E.ev_d2h[s], E.s_d2h));
-      if (staged_out) {
-        {
-          std::lock_guard<std::mutex> lk(mu);
-          enqueued = c + 1;
-        }
-        cv.notify_all();
-      }
-    }
-    return EC_OK;
-  };
-  rc = feeder();
-  if (rc) {
-    std::string keep = g_last_error;
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      abort_flag = true;
-    }
-    cv.notify_all();
-    if (drainer.joinable()) drainer.join();
-    cudaStreamSynchronize(E.s_h2d);
-    cudaStreamSynchronize(E.s_cmp);
-    cudaStreamSynchronize(E.s_d2h);
-    g_last_error = keep;
-    return rc;
-  }
-  if (drainer.joinable()) drainer.join();
-  EC_CUDA(cudaStreamSynchronize(E.s_d2h));
-  EC_CUDA(cudaStreamSynchronize(E.s_cmp));
-  EC_CUDA(cudaStreamSynchronize(E.s_h2d));
-  if (drain_rc != EC_OK) return fail(EC_ERR_CUDA, "device-to-host drain failed");
+int ec_plan_shard(int64_t count, int ndev, int idx, int64_t *lo, int64_t *hi) {
+  if (!lo || !hi) return fail(EC_ERR_ARG, "null out pointer");
+  if (count < 0 || ndev <= 0 || idx < 0 || idx >= ndev) return fail(EC_ERR_ARG, "bad shard query");
+  shard_range(count, ndev, idx, lo, hi);
   return EC_OK;
+}
+
+int ec_host_link_probe(const int *devices, int ndev, size_t bytes, int reps, double *out_gbs) {
+  return host_link_probe_impl(devices, ndev, bytes, reps, out_gbs);
 }
 
 // ---- host memory + synthetic data ----------------------------------------------------------

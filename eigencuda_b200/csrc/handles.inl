@@ -6,17 +6,20 @@
 // handles
 // ------------------------------------------------------------------------------------------
 struct StreamEngine;
+struct MultiGpu;
 
 struct ec_pipeline {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool owns_stream = true;
+  cudaEvent_t ev_order = nullptr;   // cross-stream ordering of ec_gemm operands (created on first use)
   int backend = EC_BACKEND_FP64_DMMA;
   int sm_count = 0;
   int64_t launches = 0;
   const char *last_kernel = "none";
   StagingRing staging;
   StreamEngine *engine = nullptr;
+  MultiGpu *multi = nullptr;   // child pipelines + NCCL communicators of the multi-GPU scheduler (multi_gpu.inl)
   // workers for the matrix-at-a-time staging copies of copy_to_gpu / the conversion back
   // (created on the first pageable transfer of 1 MiB or more; EC_COMPAT_THREADS=0 disables)
   bool mem_pool = false;   // device buffers of CudaMatrix come from the stream-ordered pool

@@ -85,7 +85,9 @@ struct StagingRing {
       EC_CUDA(cudaEventSynchronize(ev[s]));
       busy[s] = false;
     }
-    if (cap[s] < bytes) {
+    // slots only grow on demand and shrink again once a much smaller request follows an
+    // oversized one (a one-off large upload must not keep hundreds of MiB pinned per slot)
+    if (cap[s] < bytes || (cap[s] > ((size_t)64 << 20) && bytes <= cap[s] / 8)) {
       if (buf[s]) EC_CUDA(cudaFreeHost(buf[s]));
       buf[s] = nullptr;
       cap[s] = 0;

@@ -102,12 +102,16 @@ __global__ void __launch_bounds__(SPLIT_THREADS) ozaki_absmax_kernel(const Split
 }
 
 // 2^E from the abs-max bits: |x| * 2^-E < 1/2 for every entry of the row; NaN when the row holds a
-// non-finite value; 1 for an all-zero row.
+// non-finite value; 1 for an all-zero row.  A row whose abs-max is 2^999 or more would need an
+// exponent beyond the clamp -- the split would then see |x * 2^-E| >= 1/2 and drop the entry --
+// so such a row is poisoned with NaN like a non-finite one (its products are within a factor
+// 2^25 of overflowing FP64 anyway) instead of coming out finite and wrong.
 __device__ __forceinline__ double scale_from_amax(unsigned long long bits) {
   if (bits >= 0x7ff0000000000000ull) return __longlong_as_double(0x7ff8000000000000LL);
   if (bits == 0ull) return 1.0;
   int e = (int)((bits >> 52) & 0x7ff) - 1022 + 1;
-  e = max(-1000, min(1000, e));
+  if (e > 1000) return __longlong_as_double(0x7ff8000000000000LL);
+  e = max(-1000, e);
   return __hiloint2double((1023 + e) << 20, 0);
 }
 

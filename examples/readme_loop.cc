@@ -6,9 +6,11 @@
 //   (2) the same job as ONE tensor-level call (additive API): H2D, product and D2H of different
 //       tensor elements overlap;
 //   (3) the tensor-level call on matrices the caller keeps and has pinned in place (HostPin),
-//       results written into matrices kept across calls.
+//       results written into matrices kept across calls;
+//   (4) (3) over every GPU of the box -- the same call with a device list: the multi-GPU
+//       scheduler shards the one vector, broadcasts A with NCCL, one worker + ring per device.
 //
-// Prints one JSON object with the three rates in matrices/s.  Needs a B200; built by
+// Prints one JSON object with the rates in matrices/s.  Needs a B200; built by
 // __graft_entry__.build() into tools/bin/readme_loop and run by bench.py's extras.
 #include <chrono>
 #include <cstdio>
@@ -75,12 +77,36 @@ int main(int argc, char **argv) {
         if (rep > 0 && rate > pinned_rate) pinned_rate = rate;
       }
     }
-    const bool pinned_ok = check.isApprox(streamed[count - 1]);
+    bool pinned_ok = check.isApprox(streamed[count - 1]);
+
+    // (4) the same call over every GPU of the box (and from pageable memory, as in (2))
+    const int gpus = static_cast<int>(eigencuda::count_available_gpus());
+    double multi_pinned_rate = 0.0, multi_pageable_rate = 0.0;
+    if (gpus > 1) {
+      const std::vector<int> all_devices;   // empty = every device
+      for (int rep = 0; rep < 3; ++rep) {
+        const auto t0 = Clock::now();
+        cuda_pip.right_multiply(tensor, A, streamed, all_devices);
+        const double rate = count / seconds_since(t0);
+        if (rep > 0 && rate > multi_pageable_rate) multi_pageable_rate = rate;
+      }
+      pinned_ok = pinned_ok && check.isApprox(streamed[count - 1]);
+      eigencuda::HostPin pin_in(tensor), pin_out(streamed), pin_fixed(A);
+      for (int rep = 0; rep < 3; ++rep) {
+        const auto t0 = Clock::now();
+        cuda_pip.right_multiply(tensor, A, streamed, all_devices);
+        const double rate = count / seconds_since(t0);
+        if (rep > 0 && rate > multi_pinned_rate) multi_pinned_rate = rate;
+      }
+      pinned_ok = pinned_ok && check.isApprox(streamed[count - 1]) && check.isApprox(streamed[count - 1]);
+    }
 
     std::printf("{\"n\": %ld, \"matrices\": %zu, \"unchanged_loop_matrices_per_s\": %.1f, "
                 "\"tensor_call_pageable_matrices_per_s\": %.1f, \"tensor_call_pinned_in_place_matrices_per_s\": %.1f, "
-                "\"results_ok\": %s}\n",
-                static_cast<long>(n), count, loop_rate, stream_rate, pinned_rate,
+                "\"gpus\": %d, \"multi_gpu_call_pageable_matrices_per_s\": %.1f, "
+                "\"multi_gpu_call_pinned_in_place_matrices_per_s\": %.1f, \"results_ok\": %s}\n",
+                static_cast<long>(n), count, loop_rate, stream_rate, pinned_rate, gpus, multi_pageable_rate,
+                multi_pinned_rate,
                 (loop_ok && stream_ok && pinned_ok) ? "true" : "false");
     return (loop_ok && stream_ok && pinned_ok) ? 0 : 1;
   } catch (const std::exception &e) {

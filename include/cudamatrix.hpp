@@ -48,22 +48,35 @@ class HostPin {
   HostPin() = default;
   explicit HostPin(const Eigen::MatrixXd &m) { add(m); }
   explicit HostPin(const std::vector<Eigen::MatrixXd> &tensor) {
-    for (const Eigen::MatrixXd &m : tensor) add(m);
+    try {
+      for (const Eigen::MatrixXd &m : tensor) add(m);
+    } catch (...) {
+      release();   // the destructor does not run for a constructor that throws
+      throw;
+    }
   }
-  void add(const Eigen::MatrixXd &m) {
-    if (m.size() == 0) return;
+  // Returns whether the matrix is pinned now.  A small heap matrix can share its first or last
+  // page with a neighbour that is already pinned; such a range cannot be registered as a whole
+  // and is simply left pageable (transfers of it are staged, as without HostPin).
+  bool add(const Eigen::MatrixXd &m) {
+    if (m.size() == 0) return true;
     void *ptr = const_cast<double *>(m.data());
-    detail::throw_on_error(ec_host_register(ptr, static_cast<size_t>(m.size()) * sizeof(double)));
+    const int rc = ec_host_register(ptr, static_cast<size_t>(m.size()) * sizeof(double));
+    if (rc == EC_ERR_ARG) return false;
+    detail::throw_on_error(rc);
     _ranges.push_back(ptr);
+    return true;
   }
-  ~HostPin() {
-    for (void *ptr : _ranges) ec_host_unregister(ptr);
-  }
+  ~HostPin() { release(); }
   HostPin(const HostPin &) = delete;
   HostPin &operator=(const HostPin &) = delete;
   HostPin(HostPin &&other) noexcept : _ranges(std::move(other._ranges)) { other._ranges.clear(); }
 
  private:
+  void release() {
+    for (void *ptr : _ranges) ec_host_unregister(ptr);
+    _ranges.clear();
+  }
   std::vector<void *> _ranges;
 };
 

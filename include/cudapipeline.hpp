@@ -83,13 +83,52 @@ class CudaPipeline {
     stream_into(EC_STREAM_BASIS, A, tensor, results);
   }
 
+  // ---------------------------------------------------------------------------------------
+  // The same calls over SEVERAL GPUs of the box -- the multi-GPU scheduler
+  // (ec_tensor_stream_run_multi).  `devices` lists CUDA device indices; an empty list means every
+  // device (count_available_gpus() of them).  The caller's one vector is sharded into contiguous
+  // index ranges, one worker thread + pinned ring + three streams per device; A is uploaded once
+  // and broadcast with NCCL over NVLink; every device writes its results straight into
+  // results[i].  The pipeline's own device need not be in the list.
+  // ---------------------------------------------------------------------------------------
+  std::vector<Eigen::MatrixXd> right_multiply(const std::vector<Eigen::MatrixXd> &tensor,
+                                              const Eigen::MatrixXd &A,
+                                              const std::vector<int> &devices) const {
+    return stream(EC_STREAM_RIGHT, A, tensor, &devices);
+  }
+  void right_multiply(const std::vector<Eigen::MatrixXd> &tensor, const Eigen::MatrixXd &A,
+                      std::vector<Eigen::MatrixXd> &results, const std::vector<int> &devices) const {
+    stream_into(EC_STREAM_RIGHT, A, tensor, results, &devices);
+  }
+  std::vector<Eigen::MatrixXd> left_multiply(const Eigen::MatrixXd &A,
+                                             const std::vector<Eigen::MatrixXd> &tensor,
+                                             const std::vector<int> &devices,
+                                             bool transposeA = false) const {
+    return stream(transposeA ? EC_STREAM_LEFT_T : EC_STREAM_LEFT, A, tensor, &devices);
+  }
+  void left_multiply(const Eigen::MatrixXd &A, const std::vector<Eigen::MatrixXd> &tensor,
+                     std::vector<Eigen::MatrixXd> &results, const std::vector<int> &devices,
+                     bool transposeA = false) const {
+    stream_into(transposeA ? EC_STREAM_LEFT_T : EC_STREAM_LEFT, A, tensor, results, &devices);
+  }
+  std::vector<Eigen::MatrixXd> basis_transform(const Eigen::MatrixXd &A,
+                                               const std::vector<Eigen::MatrixXd> &tensor,
+                                               const std::vector<int> &devices) const {
+    return stream(EC_STREAM_BASIS, A, tensor, &devices);
+  }
+  void basis_transform(const Eigen::MatrixXd &A, const std::vector<Eigen::MatrixXd> &tensor,
+                       std::vector<Eigen::MatrixXd> &results, const std::vector<int> &devices) const {
+    stream_into(EC_STREAM_BASIS, A, tensor, results, &devices);
+  }
+
   ec_pipeline *handle() const { return _p; }
 
  private:
   std::vector<Eigen::MatrixXd> stream(int kind, const Eigen::MatrixXd &A,
-                                      const std::vector<Eigen::MatrixXd> &tensor) const {
+                                      const std::vector<Eigen::MatrixXd> &tensor,
+                                      const std::vector<int> *devices = nullptr) const {
     std::vector<Eigen::MatrixXd> results;
-    stream_into(kind, A, tensor, results);
+    stream_into(kind, A, tensor, results, devices);
     return results;
   }
 
@@ -97,7 +136,8 @@ class CudaPipeline {
   // that keeps -- and perhaps pins -- its result matrices across calls pays no allocation); the
   // vector is resized and the other elements are reallocated.
   void stream_into(int kind, const Eigen::MatrixXd &A, const std::vector<Eigen::MatrixXd> &tensor,
-                   std::vector<Eigen::MatrixXd> &results) const {
+                   std::vector<Eigen::MatrixXd> &results,
+                   const std::vector<int> *devices = nullptr) const {
     results.resize(tensor.size());
     if (tensor.empty()) return;
     const Index tr = tensor[0].rows(), tc = tensor[0].cols();
@@ -117,9 +157,14 @@ class CudaPipeline {
       in[i] = tensor[i].data();
       out[i] = results[i].data();
     }
-    detail::throw_on_error(ec_tensor_stream_run(_p, kind, A.data(), A.rows(), A.cols(), in.data(),
-                                                out.data(), static_cast<int64_t>(tensor.size()),
-                                                tr, tc));
+    if (devices)
+      detail::throw_on_error(ec_tensor_stream_run_multi(
+          _p, devices->data(), static_cast<int>(devices->size()), kind, A.data(), A.rows(), A.cols(),
+          in.data(), out.data(), static_cast<int64_t>(tensor.size()), tr, tc));
+    else
+      detail::throw_on_error(ec_tensor_stream_run(_p, kind, A.data(), A.rows(), A.cols(), in.data(),
+                                                  out.data(), static_cast<int64_t>(tensor.size()),
+                                                  tr, tc));
   }
 
   ec_pipeline *_p = nullptr;

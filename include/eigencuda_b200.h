@@ -147,6 +147,26 @@ int ec_tensor_stream_run(ec_pipeline *p, int kind, const double *F, int64_t f_ro
 int ec_tensor_stream_run_device(ec_pipeline *p, int kind, const double *F_dev, int64_t f_rows,
                                 int64_t f_cols, const double *tensor_dev, double *results_dev,
                                 int64_t count, int64_t t_rows, int64_t t_cols);
+/* The same job sharded over several GPUs of one box -- the multi-GPU scheduler.  `tensor` and
+ * `results` are the caller's ONE vector (README.md:58-66); device devices[g] takes the contiguous
+ * index range [g*count/ndev, (g+1)*count/ndev) with its own worker thread, pinned ring and three
+ * streams; F goes to devices[0] once and is broadcast to the others with NCCL over NVLink
+ * (libnccl.so.2 is bound at run time: EC_ERR_UNSUPPORTED when ndev > 1 and it cannot be loaded);
+ * every device DMAs its results straight into results[i]; no result exchange.  ndev == 0 means
+ * every device of the box (devices may then be NULL).  `p` carries the engine knobs and the
+ * backend and owns the per-device state, which is kept across calls.  The reference has no
+ * multi-GPU path; this replaces its unused count_available_gpus(), src/cudamatrix.cc:14-18. */
+int ec_tensor_stream_run_multi(ec_pipeline *p, const int *devices, int ndev, int kind, const double *F,
+                               int64_t f_rows, int64_t f_cols, const double *const *tensor,
+                               double *const *results, int64_t count, int64_t t_rows, int64_t t_cols);
+/* Planning query; needs no device: the index range [*lo, *hi) of a `count`-element tensor that
+ * device number idx of ndev takes in ec_tensor_stream_run_multi. */
+int ec_plan_shard(int64_t count, int ndev, int idx, int64_t *lo, int64_t *hi);
+/* Measured host-link ceiling (the roofline of the streamed configs):
+ * plain pinned cudaMemcpyAsync of `bytes` on every listed device at once, best of `reps`.
+ * out_gbs[0] = H2D only, [1] = D2H only, [2] = each direction while both run -- GB/s summed over
+ * the devices.  ndev == 0 = every device. */
+int ec_host_link_probe(const int *devices, int ndev, size_t bytes, int reps, double *out_gbs);
 /* Leave `sms` streaming multiprocessors unused by the (persistent, register-filling) GEMM kernels
  * so that concurrent kernels -- NCCL's, during the panel broadcasts of the 2D-partitioned DGEMM --
  * can run underneath them instead of queueing behind them.  0 (default) = use every SM. */

@@ -156,6 +156,9 @@ class Reference:
         L.ref_tensor_stream.restype = C.c_int
         L.ref_tensor_stream.argtypes = [C.c_int, vp, lg, lg, C.POINTER(vp), C.POINTER(vp), lg, lg,
                                         lg, C.POINTER(dbl)]
+        L.ref_tensor_stream_steps.restype = C.c_int
+        L.ref_tensor_stream_steps.argtypes = [C.c_int, vp, lg, lg, C.POINTER(vp), C.POINTER(vp), lg, lg,
+                                              lg, C.c_int, C.c_int, C.POINTER(dbl)]
         L.ref_gemm_time.restype = C.c_int
         L.ref_gemm_time.argtypes = [lg, C.c_int, C.c_int, C.POINTER(dbl)]
         L.ref_count_available_gpus.restype = lg
@@ -199,6 +202,26 @@ class Reference:
             raise ShapeMismatch("Shape mismatch in Cublas gemm")
         assert rc == 0, rc
         return res, el.value
+
+    def tensor_stream_steps(self, side, F, tensor_ptrs, count, t_shape, warmup, steps, check_index=None):
+        """Benchmark form: `tensor_ptrs` is a ctypes array of `count` host addresses of column-major
+        t_shape matrices; runs warmup + steps passes of the reference loop, returns (seconds per timed
+        pass, result matrix number `check_index` of the last pass or None)."""
+        F = _f(F)
+        tr, tc = t_shape
+        shape = (tr, F.shape[1]) if side == 0 else (F.shape[0], tc)
+        op = (C.c_void_p * count)()
+        keep = None
+        if check_index is not None:
+            keep = np.zeros(shape, order="F")
+            op[check_index] = keep.ctypes.data
+        el = (C.c_double * steps)()
+        rc = self.L.ref_tensor_stream_steps(side, F.ctypes.data, F.shape[0], F.shape[1], tensor_ptrs, op,
+                                            count, tr, tc, warmup, steps, el)
+        if rc == 1:
+            raise ShapeMismatch("Shape mismatch in Cublas gemm")
+        assert rc == 0, rc
+        return list(el), keep
 
     def gemm_time_ms(self, n, warmup=3, reps=10):
         ms = C.c_double(0)

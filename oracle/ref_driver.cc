@@ -102,6 +102,47 @@ int ref_tensor_stream(int side, const double *F, long f_rows, long f_cols,
   }
 }
 
+// The same loop for a benchmark: inputs and result vector are built once, the loop runs
+// `warmup` untimed and `steps` timed passes over the whole tensor; seconds per timed pass go to
+// elapsed[0..steps).  The results of the last pass are copied out to the caller.
+int ref_tensor_stream_steps(int side, const double *F, long f_rows, long f_cols,
+                            const double *const *tensor, double *const *results, long count,
+                            long t_rows, long t_cols, int warmup, int steps, double *elapsed) {
+  try {
+    CudaPipeline cuda_pip;
+    Eigen::MatrixXd eF = from_ptr(F, f_rows, f_cols);
+    std::vector<Eigen::MatrixXd> ts;
+    ts.reserve(count);
+    for (long i = 0; i < count; ++i) ts.push_back(from_ptr(tensor[i], t_rows, t_cols));
+    Index r_rows = side == 0 ? t_rows : f_rows, r_cols = side == 0 ? f_cols : t_cols;
+    std::vector<Eigen::MatrixXd> res(count, Eigen::MatrixXd::Zero(r_rows, r_cols));
+    CudaMatrix cuma_A{eF, cuda_pip.get_stream()};
+    CudaMatrix cuma_B{t_rows, t_cols, cuda_pip.get_stream()};
+    CudaMatrix cuma_C{r_rows, r_cols, cuda_pip.get_stream()};
+    for (int s = 0; s < warmup + steps; ++s) {
+      cudaDeviceSynchronize();
+      auto t0 = std::chrono::steady_clock::now();
+      for (Index i = 0; i < count; i++) {
+        cuma_B.copy_to_gpu(ts[i]);
+        if (side == 0)
+          cuda_pip.gemm(cuma_B, cuma_A, cuma_C);
+        else
+          cuda_pip.gemm(cuma_A, cuma_B, cuma_C);
+        res[i] = cuma_C;
+      }
+      auto t1 = std::chrono::steady_clock::now();
+      if (elapsed && s >= warmup) elapsed[s - warmup] = std::chrono::duration<double>(t1 - t0).count();
+    }
+    if (results)
+      for (long i = 0; i < count; ++i)
+        if (results[i])
+          std::memcpy(results[i], res[i].data(), sizeof(double) * static_cast<size_t>(r_rows * r_cols));
+    return 0;
+  } catch (const std::runtime_error &) {
+    return 1;
+  }
+}
+
 // Device-resident timing of the reference's gemm (== cublasDgemm NN on the legacy stream,
 // src/cudapipeline.cc:29-31) on n x n operands: `reps` back-to-back calls bracketed by CUDA events
 // on the stream cuBLAS actually runs on (the NULL stream; the reference never calls

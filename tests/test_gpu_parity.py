@@ -513,6 +513,136 @@ def test_tensor_stream_kinds(pipe, kind, pinned):
         b.close()
 
 
+# ---------------------------------------------------------------------------------------------
+# the multi-GPU tensor scheduler (ec_tensor_stream_run_multi): one vector, a device list
+# ---------------------------------------------------------------------------------------------
+def _device_sets():
+    g = ec.count_available_gpus()
+    sets = [[0]]
+    k = 2
+    while k <= g:
+        sets.append(list(range(k)))
+        k *= 2
+    if g >= 2:
+        sets.append([1, 0])
+    sets.append("all")
+    return sets
+
+
+@pytest.mark.parametrize("kind", ["right", "left", "left_t", "basis"])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_multi_gpu_tensor_stream_matches_oracle_and_single_gpu(pipe, kind, pinned):
+    """Sharding over 1, 2, 4, ... devices (as many as the box has): results within 1e-12 of the
+    oracle and BIT-identical to the single-device call; ragged shards; pinned and pageable."""
+    n, count = 144, 29
+    F = orc.fill_uniform(orc.SEED, 0, (n, n))
+    bufs = []
+    if pinned:
+        pin, pout = ec.PinnedBuffer((n, n, count)), ec.PinnedBuffer((n, n, count))
+        bufs = [pin, pout]
+        ts = [pin.array[:, :, i] for i in range(count)]
+        for i, t in enumerate(ts):
+            t[:] = orc.fill_uniform(orc.SEED, i + 1, (n, n))
+        outs = [pout.array[:, :, i] for i in range(count)]
+    else:
+        ts = [orc.fill_uniform(orc.SEED, i + 1, (n, n)) for i in range(count)]
+        outs = None
+    code = {"right": ec.EC_STREAM_RIGHT, "left": ec.EC_STREAM_LEFT, "left_t": ec.EC_STREAM_LEFT_T,
+            "basis": ec.EC_STREAM_BASIS}[kind]
+    pipe.set_stream_config(chunk_matrices=3, ring_depth=3, staging_threads=4)
+    single = [r.copy() for r in pipe.tensor_stream(code, F, ts)]
+    want = orc.tensor_stream(kind, F, ts, flavour="fast")
+    for devices in _device_sets():
+        if outs is not None:
+            for o in outs:
+                o[:] = np.nan
+        res = pipe.tensor_stream(code, F, ts, results=outs, devices=devices)
+        assert len(res) == count
+        for r, w, s1 in zip(res, want, single):
+            assert orc.rel_frobenius(r, w) <= TOL, devices
+            assert np.array_equal(r, s1), devices
+    pipe.set_stream_config(0, 0, 0)
+    for b in bufs:
+        b.close()
+
+
+def test_multi_gpu_readme_example_and_edge_cases(pipe):
+    g = json.load(open(os.path.join(GOLD, "readme_example.json")))
+    A = _mat(g["A"])
+    ts = [_mat(t) for t in g["tensor"]]
+    for devices in _device_sets():
+        res = pipe.right_multiply(ts, A, devices=devices)
+        for r, x in zip(res, g["expected"]):
+            assert orc.is_approx(r, _mat(x)), devices
+        # fewer matrices than devices, and none at all
+        one = pipe.right_multiply(ts[:1], A, devices=devices)
+        assert len(one) == 1 and orc.is_approx(one[0], _mat(g["expected"][0]))
+        assert pipe.right_multiply([], A, devices=devices) == []
+    before = pipe.launch_count()
+    with pytest.raises(RuntimeError) as e:
+        pipe.right_multiply([rnd(5, (3, 2))], rnd(6, (5, 5)), devices="all")
+    assert e.value.code == 1 and pipe.launch_count() == before     # before any device work
+    with pytest.raises(RuntimeError):
+        pipe.right_multiply(ts, A, devices=[0, 0])
+    with pytest.raises(RuntimeError):
+        pipe.right_multiply(ts, A, devices=[ec.count_available_gpus()])
+
+
+def test_multi_gpu_counts_launches_and_keeps_its_state(pipe):
+    n, count = 256, 16
+    F = orc.fill_uniform(orc.SEED, 0, (n, n))
+    ts = [orc.fill_uniform(orc.SEED, i + 1, (n, n)) for i in range(count)]
+    pipe.set_stream_config(chunk_matrices=4, ring_depth=2, staging_threads=2)
+    pipe.right_multiply(ts, F, devices="all")
+    l0 = pipe.launch_count()
+    res = pipe.right_multiply(ts, F, devices="all")
+    g = ec.count_available_gpus()
+    chunks = sum(-(-(ec.plan_shard(count, g, i)[1] - ec.plan_shard(count, g, i)[0]) // 4) for i in range(g))
+    assert pipe.launch_count() - l0 == chunks          # one batched-DGEMM launch per chunk per device
+    assert pipe.last_kernel().startswith("tma_dmma")
+    for t, r in zip(ts, res):
+        assert orc.rel_frobenius(r, orc.dgemm(t, F, flavour="ld")) <= TOL
+    pipe.set_stream_config(0, 0, 0)
+
+
+def test_multi_gpu_cpp_binary(tmp_path):
+    """tests/cpp/test_multi_gpu.cc: the scheduler from caller-side C++ (one std::vector + device list)."""
+    exe = tmp_path / "test_multi_gpu"
+    cmd = ["g++", "-std=c++14", "-O2", f"-I{ROOT}/include", f"-I{ROOT}/oracle/eigen_standin",
+           "-I/usr/local/cuda/include", f"{ROOT}/tests/cpp/test_multi_gpu.cc", "-o", str(exe),
+           f"-L{ROOT}/eigencuda_b200/lib", "-leigencuda_b200", f"-Wl,-rpath,{ROOT}/eigencuda_b200/lib"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "ALL PASSED" in res.stdout, res.stdout + res.stderr
+
+
+def test_host_link_probe_reports_a_ceiling():
+    got = ec.host_link_probe([0], nbytes=64 << 20, reps=2)
+    assert set(got) == {"h2d", "d2h", "bidir_each_way"}
+    assert all(5.0 < v < 500.0 for v in got.values()), got        # GB/s: PCIe Gen5 x16 / C2C territory
+
+
+def test_tensor_stream_rejects_unusable_result_arrays(pipe):
+    """caller-supplied outputs are validated, not written through."""
+    n = 64
+    F, ts = rnd(1, (n, n)), [rnd(2, (n, n)), rnd(3, (n, n))]
+    good = [np.empty((n, n), order="F") for _ in ts]
+    for bad in ([good[0]],                                             # too few
+                [good[0], np.empty((n, n), dtype=np.float32, order="F")],
+                [good[0], np.empty((n, n + 1), order="F")],
+                [good[0], np.empty((2 * n, n), order="F")[::2]],       # strided
+                [good[0], np.empty((n, n + 8), order="C")[:, :n]]):
+        with pytest.raises(ValueError):
+            pipe.tensor_stream(ec.EC_STREAM_RIGHT, F, ts, results=bad)
+    ro = np.empty((n, n), order="F")
+    ro.flags.writeable = False
+    with pytest.raises(ValueError):
+        pipe.tensor_stream(ec.EC_STREAM_RIGHT, F, ts, results=[good[0], ro])
+    res = pipe.tensor_stream(ec.EC_STREAM_RIGHT, F, ts, results=good)
+    assert res[0] is good[0] and orc.rel_frobenius(good[1], ts[1] @ F) <= TOL
+
+
 def test_host_pin_registers_caller_memory_in_place(pipe):
     """ec_host_register: matrices the caller already owns, pinned in place, go
     through the direct-DMA paths of copy_to_gpu / conversion / tensor stream; results identical."""

@@ -236,3 +236,36 @@ def test_cost_model_overrides(monkeypatch):
     assert ec.plan_dgemm(8192, 8192, 8192) == (S, False)
     with pytest.raises(ec.EigenCudaError):
         ec.plan_dgemm(0, 8, 8)
+
+
+def test_multi_gpu_shard_plan_covers_every_index_once():
+    """ec_plan_shard: the ranges the multi-GPU scheduler hands to its devices (same rule as
+    shard.shard_range) are contiguous, ordered, balanced to within one and cover the tensor."""
+    import eigencuda_b200 as ec
+    from eigencuda_b200 import shard
+    for count in (0, 1, 3, 7, 8, 37, 4096, 4097):
+        for ndev in (1, 2, 3, 4, 8):
+            ranges = [ec.plan_shard(count, ndev, i) for i in range(ndev)]
+            assert ranges == [shard.shard_range(count, i, ndev) for i in range(ndev)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == count
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            sizes = [hi - lo for lo, hi in ranges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ec.EigenCudaError):
+        ec.plan_shard(4, 2, 2)
+
+
+def test_tensor_stream_result_validation_needs_no_gpu():
+    """The checks on caller-supplied result arrays run before the library is called."""
+    import numpy as np
+    import eigencuda_b200 as ec
+    pipe = ec.CudaPipeline.__new__(ec.CudaPipeline)      # no device: validation must come first
+    pipe._h = None
+    n = 8
+    F, ts = np.zeros((n, n), order="F"), [np.zeros((n, n), order="F")]
+    for bad in ([], [np.zeros((n, n), dtype=np.float32, order="F")], [np.zeros((n, n), order="C")],
+                [np.zeros((n + 1, n), order="F")], [[0.0] * n]):
+        with pytest.raises(ValueError):
+            pipe.tensor_stream(ec.EC_STREAM_RIGHT, F, ts, results=bad)
+    with pytest.raises(ValueError):
+        pipe.tensor_stream(ec.EC_STREAM_RIGHT, F, ts, devices=[])
