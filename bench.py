@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-2d", action="store_true", help="skip configs[4] (the 2D-partitioned large DGEMM)")
+    ap.add_argument("--n2d", type=int, default=0, help="order of the 2D-partitioned DGEMM (0 = 16384/32768/49152/65536 at 1/2/4/8 GPUs)")
     ap.add_argument("--no-peaks", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-sample", type=int, default=0, help="matrices per step for --impl reference (0 = the e2e leg's count at N=1)")
@@ -356,11 +358,63 @@ def e2e_legs(args, ec, orc, pipe, torch, dev, world, Fh):
     return e2e, e2e_pageable
 
 
+DGEMM_2D_N = {1: 16384, 2: 32768, 4: 49152, 8: 65536}   # BASELINE.json configs[4] at 8 GPUs, scaled down below
+
+
+def dgemm_2d_leg(ec, orc, world, n=None, panel=2048, reps=2, samples=8, backend=None, schedule=None):
+    """BASELINE.json configs[4]: ONE FP64 DGEMM, 2D block-partitioned over all N GPUs with NCCL panel
+    broadcasts (ec_dgemm_2d, one process).  Operands are generated on the devices block by block
+    (34 GB per matrix at n = 65536).  Time = device time of the whole SUMMA loop, max over the GPUs
+    (CUDA events on every GPU's compute stream), best of `reps` after one warm-up pass.
+    Verification: sampled C elements against long-double dot products of generator rows/columns."""
+    import numpy as np
+    n = n or DGEMM_2D_N.get(world, 16384 * world)
+    grid = ec.DeviceGrid(list(range(world)))
+    if backend is not None:
+        grid.set_backend(backend)
+    if schedule is not None:
+        grid.set_schedule(*schedule)
+    dA, dB, dC = grid.matrix(n, n).fill_uniform(SEED, 0), grid.matrix(n, n).fill_uniform(SEED, 1), grid.matrix(n, n)
+    grid.dgemm(dA, dB, dC, panel=panel)          # warm-up: panel buffers, NCCL channels, kernel attributes
+    l0, b0 = grid.launch_count(), grid.broadcast_count()
+    times = [grid.dgemm(dA, dB, dC, panel=panel) for _ in range(reps)]
+    launches, bcasts = (grid.launch_count() - l0) // reps, (grid.broadcast_count() - b0) // reps
+    ms = min(times)
+    rng = np.random.default_rng(1234)
+    worst = 0.0
+    for _ in range(samples):
+        i, j = int(rng.integers(0, n)), int(rng.integers(0, n))
+        arow = orc.uniform_strided(SEED, 0, i, n, n).astype(np.longdouble)        # A(i, :)
+        bcol = orc.uniform_strided(SEED, 1, j * n, 1, n).astype(np.longdouble)    # B(:, j)
+        want = float(np.dot(arow, bcol))
+        scale = float(np.linalg.norm(arow.astype(np.float64)) * np.linalg.norm(bcol.astype(np.float64)))
+        worst = max(worst, abs(dC.get(i, j) - want) / scale)
+    if not worst <= 1e-12:
+        raise SystemExit(f"bench.py: dgemm_2d parity check failed, sampled relative error {worst}")
+    tf = 2.0 * n ** 3 / (ms * 1e-3) / 1e12
+    out = {"workload": f"single DGEMM n={n}, FP64, 2D block partition {grid.P}x{grid.Q} over {world} GPU(s), SUMMA panels "
+                       f"kb={panel}, NCCL panel broadcasts double-buffered against the DMMA kernel (ec_dgemm_2d, one process)",
+           "n": n, "n_gpus": world, "grid": [grid.P, grid.Q], "panel": panel, "ms": ms, "ms_all": times,
+           "tflops": tf, "tflops_per_gpu": tf / world, "frac_of_fp64_peak_per_gpu": tf / world / FP64_DATASHEET_TFLOPS,
+           "gpu_launches": launches, "nccl_panel_broadcast_groups": bcasts, "local_kernel": grid.last_kernel(),
+           "sampled_rel_err_vs_long_double": worst, "samples": samples}
+    for x in (dA, dB, dC):
+        x.close()
+    grid.close()
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank == 0:
+        # torchrun pins OMP_NUM_THREADS to 1 in every rank; the CPU baseline (numpy/OpenBLAS, rank 0
+        # only) is stated on all host cores, so give them back before numpy loads its BLAS
+        cores = str(len(os.sched_getaffinity(0)))
+        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[var] = cores
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return
@@ -477,6 +531,15 @@ def main():
         host_barrier()
         if rank == 0:
             e2e, e2e_pageable = e2e_legs(args, ec, orc, pipe, torch, dev, world, Fh)
+        host_barrier()
+
+    # ---- configs[4]: one large DGEMM 2D-partitioned over all N GPUs (rank 0 drives them) ----
+    gemm2d = None
+    if not args.no_2d:
+        torch.cuda.synchronize()
+        host_barrier()
+        if rank == 0:
+            gemm2d = dgemm_2d_leg(ec, orc, world, n=args.n2d or None)
         host_barrier()
 
     # ---- configs[1]: square DGEMM sweep on one GPU (rank 0, N=1), cuBLAS beside it at every n ----
@@ -764,7 +827,7 @@ def main():
                 "tflops": value * flops_per_matrix / 1e12,
                 "e2e": e2e, "e2e_pageable": e2e_pageable, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": roofline,
-                "cpu_baseline": cpu, "dgemm": sweep, "extras": extras, "peaks": peaks,
+                "cpu_baseline": cpu, "dgemm": sweep, "dgemm_2d": gemm2d, "extras": extras, "peaks": peaks,
                 "parity_rel_frobenius": err}
         print(json.dumps(line), flush=True)
     pipe.close()

@@ -50,6 +50,23 @@ SIGNATURES = {
                                     _i64, _i64, _i64]),
     "ec_tensor_stream_run_multi": (_int, [_vp, C.POINTER(_int), _int, _int, _dp, _i64, _i64, C.POINTER(_vp),
                                           C.POINTER(_vp), _i64, _i64, _i64]),
+    "ec_grid_create": (_int, [C.POINTER(_int), _int, _int, _int, C.POINTER(_vp)]),
+    "ec_grid_destroy": (_int, [_vp]),
+    "ec_grid_shape": (_int, [_vp, C.POINTER(_int), C.POINTER(_int)]),
+    "ec_grid_set_backend": (_int, [_vp, _int]),
+    "ec_grid_set_schedule": (_int, [_vp, _int, _int]),
+    "ec_grid_launch_count": (_i64, [_vp]),
+    "ec_grid_broadcast_count": (_i64, [_vp]),
+    "ec_grid_last_kernel": (C.c_char_p, [_vp]),
+    "ec_dist_matrix_create": (_int, [_vp, _i64, _i64, C.POINTER(_vp)]),
+    "ec_dist_matrix_destroy": (_int, [_vp]),
+    "ec_dist_matrix_upload": (_int, [_vp, _dp, _i64]),
+    "ec_dist_matrix_download": (_int, [_vp, _dp, _i64]),
+    "ec_dist_matrix_fill_uniform": (_int, [_vp, _u64, _u64]),
+    "ec_dist_matrix_get": (_int, [_vp, _i64, _i64, C.POINTER(_dbl)]),
+    "ec_dgemm_2d": (_int, [_vp, _vp, _vp, _vp, _i64, C.POINTER(_dbl)]),
+    "ec_dgemm_2d_host": (_int, [C.POINTER(_int), _int, _i64, _i64, _i64, _dp, _i64, _dp, _i64, _dp, _i64]),
+    "ec_plan_chunks": (_i64, [_i64, _i64, _int, C.POINTER(_i64), _i64]),
     "ec_plan_shard": (_int, [_i64, _int, _int, C.POINTER(_i64), C.POINTER(_i64)]),
     "ec_host_link_probe": (_int, [C.POINTER(_int), _int, C.c_size_t, _int, C.POINTER(_dbl)]),
     "ec_tensor_stream_run_device": (_int, [_vp, _int, _dp, _i64, _i64, _dp, _dp, _i64, _i64, _i64]),

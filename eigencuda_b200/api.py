@@ -263,6 +263,109 @@ class CudaPipeline:
             pass
 
 
+class DeviceGrid:
+    """P x Q grid of the box's GPUs for the 2D block-partitioned DGEMM (ec_grid; BASELINE.json
+    configs[4]).  devices: list of device indices or "all"; P = Q = 0 picks the squarest grid."""
+
+    def __init__(self, devices="all", P=0, Q=0):
+        self._h = C.c_void_p()
+        dev_arr, ndev = _device_list(devices)
+        check(lib.ec_grid_create(dev_arr, ndev, int(P), int(Q), C.byref(self._h)))
+        p, q = C.c_int(), C.c_int()
+        check(lib.ec_grid_shape(self._h, C.byref(p), C.byref(q)))
+        self.P, self.Q = p.value, q.value
+
+    def matrix(self, rows, cols):
+        return DistMatrix(self, rows, cols)
+
+    def dgemm(self, A, B, Cm, panel=0):
+        """Cm = A * B (SUMMA, NCCL panel broadcasts).  Returns device milliseconds, max over the GPUs.
+        Raises like the reference's gemm on an inner-dimension mismatch, before any device work."""
+        ms = C.c_double()
+        check(lib.ec_dgemm_2d(self._h, A._h, B._h, Cm._h, int(panel), C.byref(ms)))
+        return ms.value
+
+    def set_backend(self, backend):
+        check(lib.ec_grid_set_backend(self._h, int(backend)))
+
+    def set_schedule(self, stream_k=False, one_cta_per_tile=True):
+        check(lib.ec_grid_set_schedule(self._h, int(bool(stream_k)), int(bool(one_cta_per_tile))))
+
+    def launch_count(self):
+        return int(lib.ec_grid_launch_count(self._h))
+
+    def broadcast_count(self):
+        return int(lib.ec_grid_broadcast_count(self._h))
+
+    def last_kernel(self):
+        return lib.ec_grid_last_kernel(self._h).decode()
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.ec_grid_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DistMatrix:
+    """A rows x cols FP64 matrix cut into the grid's P x Q blocks, block (pr, pc) resident on
+    device (pr, pc), column-major (ec_dist_matrix)."""
+
+    def __init__(self, grid, rows, cols):
+        self._h = C.c_void_p()
+        self.grid, self.rows, self.cols = grid, int(rows), int(cols)
+        check(lib.ec_dist_matrix_create(grid._h, self.rows, self.cols, C.byref(self._h)))
+
+    def upload(self, a):
+        a = _as_eigen(a)
+        if a.shape != (self.rows, self.cols):
+            raise ValueError(f"expected a {self.rows} x {self.cols} matrix")
+        check(lib.ec_dist_matrix_upload(self._h, a.ctypes.data, max(a.shape[0], 1)))
+        return self
+
+    def download(self):
+        out = np.empty((self.rows, self.cols), dtype=np.float64, order="F")
+        check(lib.ec_dist_matrix_download(self._h, out.ctypes.data, max(self.rows, 1)))
+        return out
+
+    def fill_uniform(self, seed, matrix_id):
+        check(lib.ec_dist_matrix_fill_uniform(self._h, seed, matrix_id))
+        return self
+
+    def get(self, i, j):
+        v = C.c_double()
+        check(lib.ec_dist_matrix_get(self._h, int(i), int(j), C.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.ec_dist_matrix_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def dgemm_2d(A, B, devices="all"):
+    """C = A * B for host matrices through the 2D-partitioned path (ec_dgemm_2d_host)."""
+    A, B = _as_eigen(A), _as_eigen(B)
+    if A.shape[1] != B.shape[0]:
+        raise _lib.EigenCudaError(_lib.EC_ERR_SHAPE, "Shape mismatch in Cublas gemm")
+    out = np.empty((A.shape[0], B.shape[1]), dtype=np.float64, order="F")
+    dev_arr, ndev = _device_list(devices)
+    check(lib.ec_dgemm_2d_host(dev_arr, ndev, A.shape[0], B.shape[1], A.shape[1], A.ctypes.data, max(A.shape[0], 1),
+                               B.ctypes.data, max(B.shape[0], 1), out.ctypes.data, max(A.shape[0], 1)))
+    return out
+
+
 def _device_list(devices):
     """("all" | iterable of device indices) -> (ctypes int array or None, ndev); ndev 0 = every device."""
     if isinstance(devices, str):
@@ -280,6 +383,16 @@ def plan_shard(count, ndev, idx):
     lo, hi = C.c_int64(), C.c_int64()
     check(lib.ec_plan_shard(int(count), int(ndev), int(idx), C.byref(lo), C.byref(hi)))
     return lo.value, hi.value
+
+
+def plan_chunks(count, chunk, ramp=True):
+    """Chunk boundaries of a tensor-stream job (ec_plan_chunks): chunk c = [starts[c], starts[c+1])."""
+    n = lib.ec_plan_chunks(int(count), int(chunk), int(bool(ramp)), None, 0)
+    if n < 0:
+        check(_lib.EC_ERR_ARG)
+    buf = (C.c_int64 * n)()
+    lib.ec_plan_chunks(int(count), int(chunk), int(bool(ramp)), buf, n)
+    return list(buf)
 
 
 def host_link_probe(devices="all", nbytes=256 << 20, reps=5):

@@ -37,6 +37,7 @@
 #include "stream_engine.inl"    // overlapped tensor-stream engine
 #include "stream_run.inl"       // one tensor-stream job on one device (feeder + drainer)
 #include "multi_gpu.inl"        // the same job sharded over several devices of one box (NCCL broadcast)
+#include "dgemm_2d.inl"         // one huge DGEMM, 2D block-partitioned over the devices (SUMMA, NCCL panel broadcasts)
 
 // ------------------------------------------------------------------------------------------
 // C ABI
@@ -513,6 +514,113 @@ int ec_tensor_stream_run_multi(ec_pipeline *p, const int *devices, int ndev, int
                                double *const *results, int64_t count, int64_t t_rows, int64_t t_cols) {
   return tensor_stream_run_multi_impl(p, devices, ndev, kind, F, f_rows, f_cols, tensor, results, count,
                                       t_rows, t_cols);
+}
+
+// ---- 2D block-partitioned DGEMM over a device grid -------------------------------------------
+
+int ec_grid_create(const int *devices, int ndev, int P, int Q, ec_grid **out) {
+  return grid_create_impl(devices, ndev, P, Q, out);
+}
+int ec_grid_destroy(ec_grid *g) { return grid_destroy_impl(g); }
+int ec_grid_shape(const ec_grid *g, int *P, int *Q) {
+  if (!g || !P || !Q) return fail(EC_ERR_ARG, "null pointer");
+  *P = g->P;
+  *Q = g->Q;
+  return EC_OK;
+}
+int ec_grid_set_backend(ec_grid *g, int backend) {
+  if (!g) return fail(EC_ERR_ARG, "null grid");
+  for (ec_pipeline *c : g->pipes) {
+    int rc = ec_pipeline_set_backend(c, backend);
+    if (rc) return rc;
+  }
+  return EC_OK;
+}
+int ec_grid_set_schedule(ec_grid *g, int stream_k, int one_cta_per_tile) {
+  if (!g) return fail(EC_ERR_ARG, "null grid");
+  for (ec_pipeline *c : g->pipes) ec_pipeline_set_schedule(c, stream_k, one_cta_per_tile);
+  return EC_OK;
+}
+int64_t ec_grid_launch_count(const ec_grid *g) {
+  int64_t total = 0;
+  if (g)
+    for (const ec_pipeline *c : g->pipes) total += c->launches;
+  return total;
+}
+int64_t ec_grid_broadcast_count(const ec_grid *g) { return g ? g->broadcasts : 0; }
+const char *ec_grid_last_kernel(const ec_grid *g) { return g && !g->pipes.empty() ? g->pipes[0]->last_kernel : "none"; }
+
+int ec_dist_matrix_create(ec_grid *g, int64_t rows, int64_t cols, ec_dist_matrix **out) {
+  return dist_matrix_create_impl(g, rows, cols, out);
+}
+int ec_dist_matrix_destroy(ec_dist_matrix *m) { return dist_matrix_destroy_impl(m); }
+int ec_dist_matrix_upload(ec_dist_matrix *m, const double *host, int64_t ld) {
+  return dist_matrix_transfer(m, const_cast<double *>(host), ld, true);
+}
+int ec_dist_matrix_download(const ec_dist_matrix *m, double *host, int64_t ld) {
+  return dist_matrix_transfer(m, host, ld, false);
+}
+int ec_dist_matrix_fill_uniform(ec_dist_matrix *m, uint64_t seed, uint64_t matrix_id) {
+  if (!m) return fail(EC_ERR_ARG, "null matrix");
+  const ec_grid *g = m->grid;
+  for (int pr = 0; pr < g->P; ++pr)
+    for (int pc = 0; pc < g->Q; ++pc) {
+      const int i = g->dev(pr, pc);
+      const BlockGeom b = block_of(g, m->rows, m->cols, pr, pc);
+      int rc = ec_fill_uniform_block(g->pipes[i], seed, matrix_id, m->block[i], b.nrows(), b.ncols(), b.nrows(),
+                                     b.r0, b.c0, m->rows);
+      if (rc) return rc;
+    }
+  return EC_OK;
+}
+int ec_dist_matrix_get(const ec_dist_matrix *m, int64_t i, int64_t j, double *out) {
+  if (!m || !out) return fail(EC_ERR_ARG, "null pointer");
+  if (i < 0 || j < 0 || i >= m->rows || j >= m->cols) return fail(EC_ERR_ARG, "element (%lld, %lld) out of range", (long long)i, (long long)j);
+  const ec_grid *g = m->grid;
+  int64_t r0 = 0, c0 = 0;
+  const int pr = owner_of(m->rows, g->P, i, &r0), pc = owner_of(m->cols, g->Q, j, &c0);
+  const BlockGeom b = block_of(g, m->rows, m->cols, pr, pc);
+  const int d = g->dev(pr, pc);
+  DeviceGuard guard(g->devices[d]);
+  EC_CUDA(cudaMemcpyAsync(out, m->block[d] + (j - c0) * b.nrows() + (i - r0), 8, cudaMemcpyDeviceToHost, g->pipes[d]->stream));
+  EC_CUDA(cudaStreamSynchronize(g->pipes[d]->stream));
+  return EC_OK;
+}
+int ec_dgemm_2d(ec_grid *g, const ec_dist_matrix *A, const ec_dist_matrix *B, ec_dist_matrix *C, int64_t panel,
+                double *elapsed_ms) {
+  return dgemm_2d_impl(g, A, B, C, panel, elapsed_ms);
+}
+int ec_dgemm_2d_host(const int *devices, int ndev, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
+                     const double *B, int64_t ldb, double *C, int64_t ldc) {
+  if (m < 0 || n < 0 || k < 0) return fail(EC_ERR_ARG, "negative dimension");
+  ec_grid *g = nullptr;
+  int rc = ec_grid_create(devices, ndev, 0, 0, &g);
+  if (rc) return rc;
+  ec_dist_matrix *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  rc = ec_dist_matrix_create(g, m, k, &dA);
+  if (!rc) rc = ec_dist_matrix_create(g, k, n, &dB);
+  if (!rc) rc = ec_dist_matrix_create(g, m, n, &dC);
+  if (!rc) rc = ec_dist_matrix_upload(dA, A, lda);
+  if (!rc) rc = ec_dist_matrix_upload(dB, B, ldb);
+  if (!rc) rc = ec_dgemm_2d(g, dA, dB, dC, 0, nullptr);
+  if (!rc) rc = ec_dist_matrix_download(dC, C, ldc);
+  std::string keep = g_last_error;
+  ec_dist_matrix_destroy(dA);
+  ec_dist_matrix_destroy(dB);
+  ec_dist_matrix_destroy(dC);
+  ec_grid_destroy(g);
+  g_last_error = keep;
+  return rc;
+}
+
+int64_t ec_plan_chunks(int64_t count, int64_t chunk, int ramp, int64_t *starts, int64_t cap) {
+  if (count < 0 || chunk <= 0 || cap < 0 || (cap > 0 && !starts)) {
+    fail(EC_ERR_ARG, "bad chunk planning query");
+    return -1;
+  }
+  const std::vector<int64_t> plan = plan_chunks(count, chunk, ramp != 0);
+  for (size_t i = 0; i < plan.size() && (int64_t)i < cap; ++i) starts[i] = plan[i];
+  return (int64_t)plan.size();
 }
 
 int ec_plan_shard(int64_t count, int ndev, int idx, int64_t *lo, int64_t *hi) {

@@ -157,6 +157,38 @@ int stream_shape(int kind, int64_t f_rows, int64_t f_cols, int64_t t_rows, int64
   return fail(EC_ERR_ARG, "unknown tensor-stream kind %d", kind);
 }
 
+// Chunk boundaries of one job: chunk c covers matrices [starts[c], starts[c+1]).  Uniform chunks
+// of `chunk` matrices; with `ramp` the first chunks grow chunk/8, chunk/4, chunk/2 and the last
+// ones shrink the same way.  The H2D of the first chunk and the D2H of the last one cannot overlap
+// anything, so they should be short, while the chunks in between should be long: every DMA pays a
+// fixed cost, and the link only reaches its ceiling from about 64 MiB per transfer
+// (profiles/r02_engine_sweep.txt: 8 MiB chunks 39 GB/s, 32 MiB 44.6, 64-128 MiB 46 of 48 GB/s).
+std::vector<int64_t> plan_chunks(int64_t count, int64_t chunk, bool ramp) {
+  std::vector<int64_t> starts{0};
+  chunk = std::max<int64_t>(1, std::min(chunk, std::max<int64_t>(count, 1)));
+  if (!ramp || chunk < 8 || count < 6 * chunk) {
+    for (int64_t i = chunk; i < count; i += chunk) starts.push_back(i);
+    if (count > 0) starts.push_back(count);
+    return starts;
+  }
+  const int64_t steps[3] = {chunk / 8, chunk / 4, chunk / 2};
+  int64_t head = 0, tail_total = steps[0] + steps[1] + steps[2];
+  for (int64_t sz : steps) starts.push_back(head += sz);
+  while (head + chunk <= count - tail_total) starts.push_back(head += chunk);
+  // what is left -- tail_total plus a remainder below one chunk -- goes out in shrinking pieces; the
+  // remainder joins the first of them, or goes ahead of it when that would overflow a ring slot
+  const int64_t extra = count - head - tail_total;
+  int64_t first = steps[2] + extra;
+  if (first > chunk) {
+    starts.push_back(head += extra);
+    first = steps[2];
+  }
+  starts.push_back(head += first);
+  starts.push_back(head += steps[1]);
+  starts.push_back(head += steps[0]);
+  return starts;
+}
+
 // Launch the product(s) for `nb` matrices at d_in -> d_out on the pipeline's *current* stream.
 int stream_compute(ec_pipeline *p, int kind, const double *dF, int64_t f_rows, int64_t f_cols,
                    const double *d_in, double *d_out, double *d_tmp, int64_t nb, int64_t t_rows,

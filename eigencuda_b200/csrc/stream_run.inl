@@ -43,9 +43,13 @@ int tensor_stream_run_impl(ec_pipeline *p, int kind, const double *F, int64_t f_
   in_pinned = all_pinned(tensor, t_sz);
   out_pinned = all_pinned((const double *const *)results, r_sz);
   const bool staged_in = !in_pinned, staged_out = !out_pinned;
+  // chunk = matrices per ring slot (the largest chunk); default 64 MiB worth, with short first and
+  // last chunks (plan_chunks); an explicit setting gives uniform chunks of exactly that size
   int64_t chunk = p->cfg_chunk;
-  if (chunk <= 0) chunk = std::max<int64_t>(1, ((int64_t)32 << 20) / (8 * std::max(t_sz, r_sz)));
+  const bool ramp = chunk <= 0;
+  if (chunk <= 0) chunk = std::max<int64_t>(1, ((int64_t)64 << 20) / (8 * std::max(t_sz, r_sz)));
   chunk = std::min(chunk, count);
+  const std::vector<int64_t> starts = plan_chunks(count, chunk, ramp);
   const int ring = p->cfg_ring > 0 ? p->cfg_ring : 3;
   int threads = p->cfg_threads;
   if (threads <= 0) threads = std::max(2u, std::min(16u, std::thread::hardware_concurrency()));
@@ -86,7 +90,7 @@ int tensor_stream_run_impl(ec_pipeline *p, int kind, const double *F, int64_t f_
   EC_CUDA(cudaEventRecord(E.ev_fixed, E.s_h2d));
   EC_CUDA(cudaStreamWaitEvent(E.s_cmp, E.ev_fixed, 0));
 
-  const int64_t nchunks = (count + chunk - 1) / chunk;
+  const int64_t nchunks = (int64_t)starts.size() - 1;
 
   // ---- drainer (pageable results only) ----
   std::mutex mu;
@@ -108,7 +112,7 @@ int tensor_stream_run_impl(ec_pipeline *p, int kind, const double *F, int64_t f_
         if (cudaEventSynchronize(E.ev_d2h[s]) != cudaSuccess) {
           drain_rc = EC_ERR_CUDA;
         } else {
-          const int64_t i0 = c * chunk, nb = std::min(chunk, count - i0);
+          const int64_t i0 = starts[c], nb = starts[c + 1] - i0;
           TraceRange trace_chunk("deliver chunk (pinned -> caller)");
           const char *src = (const char *)E.pin_out[s];
           // split every matrix into a few pieces so the pool stays busy even for small chunks
@@ -134,7 +138,7 @@ int tensor_stream_run_impl(ec_pipeline *p, int kind, const double *F, int64_t f_
   auto feeder = [&]() -> int {
     for (int64_t c = 0; c < nchunks; ++c) {
       const int s = (int)(c % ring);
-      const int64_t i0 = c * chunk, nb = std::min(chunk, count - i0);
+      const int64_t i0 = starts[c], nb = starts[c + 1] - i0;
       // H2D
       if (staged_in) {
         if (c >= ring) EC_CUDA(cudaEventSynchronize(E.ev_h2d[s]));  // pinned_in[s] consumed

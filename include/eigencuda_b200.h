@@ -162,6 +162,12 @@ int ec_tensor_stream_run_multi(ec_pipeline *p, const int *devices, int ndev, int
 /* Planning query; needs no device: the index range [*lo, *hi) of a `count`-element tensor that
  * device number idx of ndev takes in ec_tensor_stream_run_multi. */
 int ec_plan_shard(int64_t count, int ndev, int idx, int64_t *lo, int64_t *hi);
+/* Planning query; needs no device: the chunk boundaries the tensor-stream engine uses for a job of
+ * `count` matrices with at most `chunk` matrices per device chunk; ramp != 0 = the default plan
+ * (short first and last chunks), 0 = uniform chunks (what an explicit
+ * ec_pipeline_set_stream_config gives).  Writes up to `cap` boundaries (chunk c covers
+ * [starts[c], starts[c+1])) and returns how many there are (number of chunks + 1), -1 on error. */
+int64_t ec_plan_chunks(int64_t count, int64_t chunk, int ramp, int64_t *starts, int64_t cap);
 /* Measured host-link ceiling (the roofline of the streamed configs):
  * plain pinned cudaMemcpyAsync of `bytes` on every listed device at once, best of `reps`.
  * out_gbs[0] = H2D only, [1] = D2H only, [2] = each direction while both run -- GB/s summed over
@@ -181,6 +187,44 @@ int ec_pipeline_set_schedule(ec_pipeline *p, int stream_k, int one_cta_per_tile)
 /* Engine knobs: matrices per device chunk, ring depth, staging worker threads (0 = default). */
 int ec_pipeline_set_stream_config(ec_pipeline *p, int chunk_matrices, int ring_depth,
                                   int staging_threads);
+
+/* ---- one very large DGEMM, 2D block-partitioned over the GPUs of one box ------------------- */
+
+/* BASELINE.json configs[4] (n = 65536 on 8 GPUs).  The reference's gemm is one cublasDgemm on one
+ * device with its dimensions narrowed to int (src/cudapipeline.cc:29-31): a product whose
+ * operands do not fit one device, or whose element count passes 2^31, cannot be expressed there.
+ * Here: a P x Q device grid (ec_grid; P = Q = 0 picks the squarest grid, ndev == 0 every device),
+ * matrices cut into P x Q blocks with block (pr, pc) resident on device devices[pr*Q + pc]
+ * (ec_dist_matrix), and ec_dgemm_2d: C = A * B by SUMMA -- per k-panel the owning grid column
+ * broadcasts its panel of A along the grid rows and the owning grid row its panel of B along the
+ * grid columns (NCCL over NVLink, on a side stream, double-buffered), every device accumulates
+ * C(pr,pc) += Apanel * Bpanel with the library's DGEMM kernel.  One process, one host thread.
+ * EC_ERR_SHAPE on an inner-dimension mismatch, before any device work, like the reference's gemm.
+ * `panel` = k-panel width (0 = 2048); *elapsed_ms (optional) = device time, max over the GPUs. */
+typedef struct ec_grid ec_grid;
+typedef struct ec_dist_matrix ec_dist_matrix;
+int ec_grid_create(const int *devices, int ndev, int P, int Q, ec_grid **out);
+int ec_grid_destroy(ec_grid *g);
+int ec_grid_shape(const ec_grid *g, int *P, int *Q);
+int ec_grid_set_backend(ec_grid *g, int backend);
+int ec_grid_set_schedule(ec_grid *g, int stream_k, int one_cta_per_tile);
+int64_t ec_grid_launch_count(const ec_grid *g);
+int64_t ec_grid_broadcast_count(const ec_grid *g);
+const char *ec_grid_last_kernel(const ec_grid *g);
+int ec_dist_matrix_create(ec_grid *g, int64_t rows, int64_t cols, ec_dist_matrix **out);
+int ec_dist_matrix_destroy(ec_dist_matrix *m);
+/* whole column-major host matrix (leading dimension ld) <-> blocks; complete on return */
+int ec_dist_matrix_upload(ec_dist_matrix *m, const double *host, int64_t ld);
+int ec_dist_matrix_download(const ec_dist_matrix *m, double *host, int64_t ld);
+/* every block synthesised where it lives: element (i, j) = generator value at index j*rows + i
+ * (ec_fill_uniform_block) -- the n = 65536 operands are 34 GB each, more than the host holds */
+int ec_dist_matrix_fill_uniform(ec_dist_matrix *m, uint64_t seed, uint64_t matrix_id);
+int ec_dist_matrix_get(const ec_dist_matrix *m, int64_t i, int64_t j, double *out);
+int ec_dgemm_2d(ec_grid *g, const ec_dist_matrix *A, const ec_dist_matrix *B, ec_dist_matrix *C, int64_t panel,
+                double *elapsed_ms);
+/* convenience: host operands in, host result out, on a grid made and destroyed inside the call */
+int ec_dgemm_2d_host(const int *devices, int ndev, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
+                     const double *B, int64_t ldb, double *C, int64_t ldc);
 
 /* ---- host memory + synthetic data helpers ------------------------------------------------- */
 

@@ -617,6 +617,75 @@ def test_multi_gpu_cpp_binary(tmp_path):
     assert res.returncode == 0 and "ALL PASSED" in res.stdout, res.stdout + res.stderr
 
 
+# ---------------------------------------------------------------------------------------------
+# one large DGEMM, 2D block-partitioned over a device grid (ec_dgemm_2d, BASELINE.json configs[4])
+# ---------------------------------------------------------------------------------------------
+def _grids():
+    g = ec.count_available_gpus()
+    out = [([0], 1, 1)]
+    if g >= 2:
+        out += [([0, 1], 1, 2), ([0, 1], 2, 1), ([1, 0], 0, 0)]
+    if g >= 4:
+        out += [([0, 1, 2, 3], 2, 2), ([0, 1, 2, 3], 1, 4), ([0, 1, 2, 3], 4, 1)]
+    if g >= 8:
+        out += [(list(range(8)), 2, 4), (list(range(8)), 4, 2)]
+    return out
+
+
+@pytest.mark.parametrize("shape,panel", [((640, 512, 768), 128), ((515, 389, 1030), 100), ((96, 1200, 64), 0),
+                                         ((1, 1, 1), 0), ((300, 200, 7), 3)])
+def test_dgemm_2d_matches_oracle_on_every_grid(shape, panel):
+    """SUMMA over 1x1, 1x2, 2x1, 2x2, 1x4, 4x1, 2x4, 4x2 (what the box has): results within 1e-12 of
+    the long-double oracle, ragged blocks and panels, host upload / download round trip."""
+    m, n, k = shape
+    A, B = rnd(11, (m, k)), rnd(12, (k, n))
+    want = orc.dgemm(A, B, flavour="ld")
+    for devices, P, Q in _grids():
+        grid = ec.DeviceGrid(devices, P, Q)
+        dA, dB, dC = grid.matrix(m, k).upload(A), grid.matrix(k, n).upload(B), grid.matrix(m, n)
+        assert np.array_equal(dA.download(), A)                         # blocks round-trip bit-exactly
+        l0, b0 = grid.launch_count(), grid.broadcast_count()
+        ms = grid.dgemm(dA, dB, dC, panel=panel)
+        got = dC.download()
+        assert orc.rel_frobenius(got, want) <= TOL, (devices, P, Q)
+        assert grid.launch_count() > l0 and ms >= 0.0
+        if grid.P * grid.Q > 1:
+            assert grid.broadcast_count() > b0                          # the panels went through NCCL
+        assert dC.get(m - 1, n - 1) == got[m - 1, n - 1] and dC.get(0, 0) == got[0, 0]
+        for x in (dA, dB, dC):
+            x.close()
+        grid.close()
+
+
+def test_dgemm_2d_generated_operands_and_shape_errors():
+    """Operands synthesised block by block on their owners equal the global generator; the product
+    of generated operands matches sampled long-double dot products (how n = 65536 is verified)."""
+    n = 1536
+    grid = ec.DeviceGrid("all")
+    dA, dB, dC = grid.matrix(n, n).fill_uniform(orc.SEED, 0), grid.matrix(n, n).fill_uniform(orc.SEED, 1), grid.matrix(n, n)
+    assert np.array_equal(dA.download(), orc.fill_uniform(orc.SEED, 0, (n, n)))
+    grid.dgemm(dA, dB, dC, panel=256)
+    rng = np.random.default_rng(5)
+    for _ in range(12):
+        i, j = int(rng.integers(0, n)), int(rng.integers(0, n))
+        arow = orc.uniform_strided(orc.SEED, 0, i, n, n).astype(np.longdouble)
+        bcol = orc.uniform_strided(orc.SEED, 1, j * n, 1, n).astype(np.longdouble)
+        want = float(np.dot(arow, bcol))
+        scale = float(np.linalg.norm(arow.astype(np.float64)) * np.linalg.norm(bcol.astype(np.float64)))
+        assert abs(dC.get(i, j) - want) <= 1e-13 * scale
+    bad = grid.matrix(n + 1, 8)
+    before = grid.launch_count()
+    with pytest.raises(RuntimeError) as e:
+        grid.dgemm(dA, bad, dC)
+    assert e.value.code == 1 and grid.launch_count() == before          # before any device work
+    with pytest.raises(RuntimeError):
+        ec.DeviceGrid([0], 2, 2)
+    # host-pointer convenience form
+    A, B = rnd(21, (200, 300)), rnd(22, (300, 100))
+    assert orc.rel_frobenius(ec.dgemm_2d(A, B), orc.dgemm(A, B, flavour="ld")) <= TOL
+    grid.close()
+
+
 def test_host_link_probe_reports_a_ceiling():
     got = ec.host_link_probe([0], nbytes=64 << 20, reps=2)
     assert set(got) == {"h2d", "d2h", "bidir_each_way"}

@@ -269,3 +269,24 @@ def test_tensor_stream_result_validation_needs_no_gpu():
             pipe.tensor_stream(ec.EC_STREAM_RIGHT, F, ts, results=bad)
     with pytest.raises(ValueError):
         pipe.tensor_stream(ec.EC_STREAM_RIGHT, F, ts, devices=[])
+
+
+def test_chunk_plan_covers_the_tensor_with_short_ends():
+    """ec_plan_chunks: boundaries strictly increase from 0 to count, no chunk exceeds the ring slot,
+    and the default plan starts and ends with chunks an eighth of the slot (the transfers that
+    nothing can overlap)."""
+    import eigencuda_b200 as ec
+    for count in (0, 1, 5, 31, 32, 33, 191, 192, 193, 1000, 4096, 4097):
+        for chunk in (1, 4, 7, 8, 32, 33, 100):
+            for ramp in (False, True):
+                starts = ec.plan_chunks(count, chunk, ramp)
+                assert starts[0] == 0 and starts[-1] == count
+                sizes = [b - a for a, b in zip(starts, starts[1:])]
+                assert all(0 < sz <= chunk for sz in sizes), (count, chunk, ramp, sizes)
+                if not ramp:
+                    assert all(sz == chunk for sz in sizes[:-1])
+                elif chunk >= 8 and count >= 6 * chunk:
+                    assert sizes[0] == chunk // 8 and sizes[1] == chunk // 4 and sizes[2] == chunk // 2
+                    assert sizes[-1] <= max(chunk // 8, 1) + 0 or sizes[-1] <= chunk // 2
+                    assert max(sizes) == chunk
+                    assert len(sizes) <= count // chunk + 7
