@@ -361,7 +361,7 @@ def e2e_legs(args, ec, orc, pipe, torch, dev, world, Fh):
 DGEMM_2D_N = {1: 16384, 2: 32768, 4: 49152, 8: 65536}   # BASELINE.json configs[4] at 8 GPUs, scaled down below
 
 
-def dgemm_2d_leg(ec, orc, world, n=None, panel=2048, reps=2, samples=8, backend=None, schedule=None):
+def dgemm_2d_leg(ec, orc, world, n=None, panel=4096, reps=2, samples=8, backend=None, schedule=None):
     """BASELINE.json configs[4]: ONE FP64 DGEMM, 2D block-partitioned over all N GPUs with NCCL panel
     broadcasts (ec_dgemm_2d, one process).  Operands are generated on the devices block by block
     (34 GB per matrix at n = 65536).  Time = device time of the whole SUMMA loop, max over the GPUs

@@ -46,6 +46,7 @@ struct ec_dist_matrix {
   ec_grid *grid = nullptr;
   int64_t rows = 0, cols = 0;
   std::vector<double *> block;              // per device
+  std::vector<int> devices;                 // copy of the grid's list: a matrix may be released after its grid
 };
 
 namespace {
@@ -138,7 +139,14 @@ int grid_create_impl(const int *devices, int ndev, int P, int Q, ec_grid **out) 
     rc = ec_pipeline_create(devs[i], &g->pipes[i]);
     if (rc) break;
     cudaSetDevice(devs[i]);
-    cudaError_t e = cudaStreamCreateWithFlags(&g->comm[i], cudaStreamNonBlocking);
+    // The side stream outranks the compute stream: when a panel product and the broadcast of the
+    // next panel become runnable at the same moment, the broadcast's few CTAs must get the first
+    // SMs that free up -- at equal priority the block scheduler keeps feeding the product's
+    // 32768 CTAs and the broadcast only starts once they run out, i.e. serialised behind it
+    // (measured: 88 % instead of 95 % of peak per GPU on 2 GPUs).
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaError_t e = cudaStreamCreateWithPriority(&g->comm[i], cudaStreamNonBlocking, prio_hi);
     for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
       e = cudaEventCreateWithFlags(&g->ready[b][i], cudaEventDisableTiming);
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->freed[b][i], cudaEventDisableTiming);
@@ -202,8 +210,8 @@ int dist_matrix_destroy_impl(ec_dist_matrix *m) {
   if (!m) return EC_OK;
   for (size_t i = 0; i < m->block.size(); ++i)
     if (m->block[i]) {
-      DeviceGuard guard(m->grid->devices[i]);
-      cudaFree(m->block[i]);
+      DeviceGuard guard(m->devices[i]);
+      cudaFree(m->block[i]);   // synchronises with outstanding work on the block
     }
   delete m;
   return EC_OK;
@@ -219,6 +227,7 @@ int dist_matrix_create_impl(ec_grid *g, int64_t rows, int64_t cols, ec_dist_matr
   m->rows = rows;
   m->cols = cols;
   m->block.assign(g->devices.size(), nullptr);
+  m->devices = g->devices;
   for (int pr = 0; pr < g->P; ++pr)
     for (int pc = 0; pc < g->Q; ++pc) {
       const BlockGeom b = block_of(g, rows, cols, pr, pc);
@@ -277,7 +286,7 @@ int dgemm_2d_impl(ec_grid *g, const ec_dist_matrix *A, const ec_dist_matrix *B, 
   if (elapsed_ms) *elapsed_ms = 0.0;
   if (m == 0 || n == 0) return EC_OK;
   const int P = g->P, Q = g->Q, G = P * Q;
-  const int64_t kb = panel > 0 ? panel : 2048;
+  const int64_t kb = panel > 0 ? panel : 4096;
   const std::vector<std::pair<int64_t, int64_t>> panels = summa_panels(k, P, Q, kb);
   int64_t wmax = 0;
   for (const auto &pn : panels) wmax = std::max(wmax, pn.second - pn.first);

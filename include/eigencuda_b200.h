@@ -200,7 +200,7 @@ int ec_pipeline_set_stream_config(ec_pipeline *p, int chunk_matrices, int ring_d
  * grid columns (NCCL over NVLink, on a side stream, double-buffered), every device accumulates
  * C(pr,pc) += Apanel * Bpanel with the library's DGEMM kernel.  One process, one host thread.
  * EC_ERR_SHAPE on an inner-dimension mismatch, before any device work, like the reference's gemm.
- * `panel` = k-panel width (0 = 2048); *elapsed_ms (optional) = device time, max over the GPUs. */
+ * `panel` = k-panel width (0 = 4096); *elapsed_ms (optional) = device time, max over the GPUs. */
 typedef struct ec_grid ec_grid;
 typedef struct ec_dist_matrix ec_dist_matrix;
 int ec_grid_create(const int *devices, int ndev, int P, int Q, ec_grid **out);

@@ -17,7 +17,7 @@ from oracle import oracle_py as orc
 ap = argparse.ArgumentParser()
 ap.add_argument("--gpus", type=int, default=ec.count_available_gpus())
 ap.add_argument("--size", type=int, default=0)
-ap.add_argument("--panel", type=int, default=2048)
+ap.add_argument("--panel", type=int, default=4096)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--backend", default="native", choices=["native", "ozaki"])
 ap.add_argument("--schedule", default="default", choices=["default", "persistent", "tile"])
