@@ -17,7 +17,7 @@
 // The broadcasts of panel t+1 run on a side stream per device, double-buffered against the product
 // of panel t.  One host thread drives all devices (everything is asynchronous); NCCL calls of one
 // panel are grouped.  The NCCL communicators are created with a cap on the CTAs their kernels may
-// use (EC_2D_NCCL_CTAS, default 4): the panels need ~10 GB/s per GPU, a fraction of what one
+// use (EC_2D_NCCL_CTAS, default 8): the panels need ~10 GB/s per GPU, a fraction of what one
 // channel moves over NVLink, and every SM NCCL holds is an SM the persistent GEMM grid cannot use.
 //
 // Why not a kernel that TMA-loads the panels straight from the peers: peer addresses bypass the
@@ -36,7 +36,7 @@ struct ec_grid {
   std::vector<double *> bufA[2], bufB[2];   // panel double buffers per device
   std::vector<size_t> bufA_bytes, bufB_bytes;
   std::vector<cudaEvent_t> ready[2], freed[2], t0, t1;
-  int nccl_ctas = 4;
+  int nccl_ctas = 8;
   int64_t broadcasts = 0;
 
   int dev(int pr, int pc) const { return pr * Q + pc; }

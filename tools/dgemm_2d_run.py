@@ -2,7 +2,7 @@
 (ec_dgemm_2d: one process, NCCL panel broadcasts).  Same leg as bench.py's `dgemm_2d` block.
     python tools/dgemm_2d_run.py [--gpus N] [--size n] [--panel kb] [--backend native|ozaki]
                                  [--schedule persistent|tile]
-Environment: EC_2D_NCCL_CTAS caps the CTAs NCCL's broadcast kernels may use (default 4, 0 = NCCL's own choice)."""
+Environment: EC_2D_NCCL_CTAS caps the CTAs NCCL's broadcast kernels may use (default 8, 0 = NCCL's own choice)."""
 import argparse
 import json
 import os
@@ -25,5 +25,5 @@ a = ap.parse_args()
 sched = {"default": None, "persistent": (True, False), "tile": (False, True)}[a.schedule]
 out = bench.dgemm_2d_leg(ec, orc, a.gpus, n=a.size or None, panel=a.panel, reps=a.reps,
                          backend=ec.EC_BACKEND_OZAKI_I8 if a.backend == "ozaki" else None, schedule=sched)
-out.update({"backend": a.backend, "schedule": a.schedule, "nccl_ctas": os.environ.get("EC_2D_NCCL_CTAS", "4 (default)")})
+out.update({"backend": a.backend, "schedule": a.schedule, "nccl_ctas": os.environ.get("EC_2D_NCCL_CTAS", "8 (default)")})
 print(json.dumps(out), flush=True)
