@@ -64,9 +64,12 @@ int dgemm_dispatch(ec_pipeline *p, int transa, int transb, int64_t m, int64_t n,
                                       "tma_dmma_TN_xs_sk", "tma_dmma_TT_xs_sk", "tma_dmma_NN_xs_sk", "tma_dmma_NT_xs_sk"};
     static const char *const nT[8] = {"tma_dmma_TN_t", "tma_dmma_TT_t", "tma_dmma_NN_t", "tma_dmma_NT_t",
                                       "tma_dmma_TN_t_sk", "tma_dmma_TT_t_sk", "tma_dmma_NN_t_sk", "tma_dmma_NT_t_sk"};
+    static const char *const nN[8] = {"tma_dmma_TN_n", "tma_dmma_TT_n", "tma_dmma_NN_n", "tma_dmma_NT_n",
+                                      "tma_dmma_TN_n_sk", "tma_dmma_TT_n_sk", "tma_dmma_NN_n_sk", "tma_dmma_NT_n_sk"};
     const TileChoice ch = choose_tile(p, m, n, k, batch);
     switch (ch.tile) {
       case TILE_S: return run_tma_dmma<ec::CfgS>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nS);
+      case TILE_N: return run_tma_dmma<ec::CfgN>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nN);
       case TILE_T: return run_tma_dmma<ec::CfgT>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nT);
       case TILE_XS: return run_tma_dmma<ec::CfgXS>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nX);
       default: return run_tma_dmma<ec::CfgL>(p, oa, ob, m, n, k, alpha, beta, C, ldc, stride_c, stride_a, stride_b, batch, ch.sk, nL);

@@ -70,6 +70,8 @@ using CfgL  = TileCfg<128, 128, 64, 32, 5, 1, true>;    // 8 consumer warps, 160
 using CfgS  = TileCfg< 64,  64, 32, 32, 4, 2, false>;   // 4 consumer warps,  64 KiB, 2 CTAs/SM
 using CfgXS = TileCfg< 64,  32, 32, 16, 4, 3, false>;   // 4 consumer warps,  48 KiB, 3 CTAs/SM
 using CfgT  = TileCfg< 32,  32, 16, 16, 4, 5, false>;   // 4 consumer warps,  33 KiB, 5 CTAs/SM (80 regs; 6 would spill): tensors of matrices of 32 x 32 and less
+using CfgN  = TileCfg<128,  16, 32, 16, 4, 3, false>;   // 4 consumer warps,  73 KiB, 3 CTAs/SM: skinny products with at most 16 columns --
+                                                        // a 32-wide tile would spend half its DMMAs on padding, which is what bounds these HBM-bound shapes
 // (A 128x64 / 2 CTAs-per-SM variant and register-split variants of the small tiles were measured
 //  and lost everywhere -- profiles/r01_tile_sweep*.json -- so they are not built.)
 
@@ -90,6 +92,7 @@ struct GemmParams {
   unsigned *sk_flags;      // gridDim.x flags; flag[c] == sk_epoch <=> CTA c's partial is published
   unsigned sk_epoch;       // unique per launch, so flags never need resetting
   int c_vec2;              // C base, ldc and batch stride are 16-byte aligned: row pairs may use 16 B stores
+  int pdl_trigger;         // where griddepcontrol.launch_dependents is issued: 0 never, 1 after the wait, 2 at kernel start, 3 before the first epilogue
   int sk_sms;              // SM count: CTAs b and b + sk_sms share an SM and get ADJACENT stream-K
                            // ranges, so their tile boundaries (epilogues) fall at different times
 };
@@ -165,6 +168,16 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+// Programmatic dependent launch (PDL).  launch_dependents: the next kernel of the stream may be
+// scheduled from now on (it becomes resident where SM resources allow and runs its prologue
+// underneath this grid); grid_dependency_wait: blocks until every prerequisite grid has completed
+// and its memory is visible.  Both are no-ops for a launch without the PDL attribute.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_grid_dependency_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 // named barrier over the consumer warps only (barrier 0 is __syncthreads)
 __device__ __forceinline__ void consumer_bar_sync(int nthreads) {
@@ -318,6 +331,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // PDL: the next product of the stream (the compat loop issues them back to back) may set itself
+  // up while this one runs -- its launch latency, barrier init and descriptor fetch disappear
+  // behind this grid.  Everything up to the wait below touches no global memory.
+  if (p.pdl_trigger == 2) pdl_launch_dependents();
+
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
@@ -332,6 +350,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
     tma_prefetch_desc(&tmB);
   }
   __syncthreads();
+  // from here on global memory is read (operands, beta * C, stream-K flags) and written: the
+  // kernels queued before this one must be complete
+  pdl_grid_dependency_wait();
+  // Trigger only now, with the predecessor gone: at most ONE dependent grid is ever resident
+  // underneath a running one (triggering before the wait lets a whole queue of launches pile
+  // into the SMs' free slots).
+  if (p.pdl_trigger == 1) pdl_launch_dependents();
 
   const int kblocks = (int)((p.K + BK - 1) / BK);
   const int tiles_per_problem = p.tiles_m * p.tiles_n;
@@ -491,6 +516,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
     }
 
     // ---- epilogue: registers -> global, C = alpha*acc + beta*C ----
+    if (p.pdl_trigger == 3) pdl_launch_dependents();
     const int b = (int)(sg.tile / tiles_per_problem);
     const int r = (int)(sg.tile - (int64_t)b * tiles_per_problem);
     const int m0 = (r % p.tiles_m) * BM;

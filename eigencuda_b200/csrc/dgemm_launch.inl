@@ -104,6 +104,7 @@ int launch_tma_dmma(ec_pipeline *p, const CUtensorMap &tmA, const CUtensorMap &t
   gp.sk_workspace = nullptr;
   gp.sk_flags = nullptr;
   gp.sk_epoch = 0;
+  gp.pdl_trigger = p->pdl;
   // Stream-K region: the tiles of the last, partial wave plus (when there is one) one full wave,
   // so that every CTA gets between one and two tiles' worth of k-iterations in the region.
   const int64_t rem = gp.total_tiles % slots;
@@ -132,7 +133,23 @@ int launch_tma_dmma(ec_pipeline *p, const CUtensorMap &tmA, const CUtensorMap &t
     EC_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(Cfg::THREADS), args,
                                         (size_t)Cfg::SMEM_BYTES, p->stream));
   } else {
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, p->stream>>>(tmA, tmB, gp);
+    // programmatic dependent launch: this grid may become resident while its predecessor in the
+    // stream is still running; the kernel waits (griddepcontrol.wait) before it touches memory
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = p->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    // Only for grids that fill at most half of the resident slots: the dependent grid is placed
+    // into whatever slots its predecessor leaves free, and once the two do not both fit that
+    // placement is lopsided -- some SMs end up with five CTAs of the new grid, others with none
+    // (measured, back to back: n = 512 14.5 -> 13.1 us with PDL, but n = 640 22.7 -> 33.6 us).
+    cfg.numAttrs = (p->pdl && (int64_t)grid * 2 <= slots) ? 1 : 0;
+    EC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, gp));
   }
   EC_CUDA(cudaGetLastError());
   p->launches++;
@@ -173,7 +190,7 @@ int run_tma_dmma(ec_pipeline *p, const Operand &oa, const Operand &ob, int64_t m
 // does ceil(tiles / SMs) tiles, under stream-K every SM does tiles / SMs of them plus one
 // workspace round trip -- and (b) per-tile overhead and main-loop efficiency, which get worse
 // as tiles shrink.  Cost model in SM clocks, fitted to profiles/r01_tile_sweep*.json.
-enum { TILE_AUTO = 0, TILE_L = 1, TILE_S = 2, TILE_XS = 3, TILE_T = 4 };
+enum { TILE_AUTO = 0, TILE_L = 1, TILE_S = 2, TILE_XS = 3, TILE_T = 4, TILE_N = 5 };
 
 struct TileChoice { int tile; bool sk; };
 
@@ -196,16 +213,18 @@ TileChoice choose_tile(const ec_pipeline *p, int64_t m, int64_t n, int64_t k, in
   // rate: it tops out near 0.72 however many CTAs share the SM (26-30 TFLOP/s), but it is the only
   // shape that fills the machine for n <= 640 and wastes nothing on matrices of 32 x 32 and less.
   struct Cand { int id, bm, bn, ctas; double eff[6], overhead, fixup; };
-  const Cand cands[4] = {{TILE_L, 128, 128, 1, {0.987, 0.987, 0.987, 0.987, 0.987, 0.987}, 2300.0, 30000.0},
+  const Cand cands[5] = {{TILE_L, 128, 128, 1, {0.987, 0.987, 0.987, 0.987, 0.987, 0.987}, 2300.0, 30000.0},
                          {TILE_S, 64, 64, 2, {0.59, 0.955, 0.955, 0.955, 0.955, 0.955}, 1200.0, 17000.0},
                          {TILE_XS, 64, 32, 3, {0.50, 0.76, 0.80, 0.80, 0.80, 0.80}, 450.0, 20000.0},
-                         {TILE_T, 32, 32, 5, {0.30, 0.58, 0.68, 0.72, 0.72, 0.72}, 250.0, 20000.0}};
+                         {TILE_T, 32, 32, 5, {0.30, 0.58, 0.68, 0.72, 0.72, 0.72}, 250.0, 20000.0},
+                         // 128x16: the same MACs per tile as 64x32; only ever cheaper when N <= 16 halves the tile count
+                         {TILE_N, 128, 16, 3, {0.50, 0.76, 0.80, 0.80, 0.80, 0.80}, 450.0, 20000.0}};
   const double kpad = (double)((k + 15) / 16 * 16);
   const int64_t kblocks = (k + 15) / 16;
   double best = 1e300;
   TileChoice pick{TILE_L, false};
   for (const Cand &c : cands) {
-    if (force >= TILE_L && force <= TILE_T && c.id != force) continue;
+    if (force >= TILE_L && force <= TILE_N && c.id != force) continue;
     const int64_t tiles = ((m + c.bm - 1) / c.bm) * ((n + c.bn - 1) / c.bn) * batch;
     const int sms = p->sm_count - p->sm_margin;
     const int64_t slots = (int64_t)sms * c.ctas;

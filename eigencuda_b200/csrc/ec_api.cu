@@ -74,6 +74,7 @@ static int pipeline_create_impl(int device, cudaStream_t external, bool use_exte
                 prop.major, prop.minor);
   ec_pipeline *p = new ec_pipeline();
   p->device = dev;
+  if (const char *e = std::getenv("EC_PDL")) p->pdl = std::max(0, std::min(3, std::atoi(e)));
   p->sm_count = prop.multiProcessorCount;
   if (use_external) {
     p->stream = external;

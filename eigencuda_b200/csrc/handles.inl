@@ -33,6 +33,7 @@ struct ec_pipeline {
   int stream_k = 1;   // 0 disables the stream-K schedule (EC_STREAM_K=0)
   int sm_margin = 0;  // SMs left free for concurrent kernels (NCCL during SUMMA)
   int one_cta_per_tile = 0;  // non-persistent launch for long tiles (shared-GPU friendly)
+  int pdl = 1;               // programmatic dependent launch of the GEMM kernels (EC_PDL=0 turns it off)
   // small direct-mapped cache of encoded tensor maps: the compat loop and every tensor-stream
   // chunk reuse the same few device buffers, and cuTensorMapEncodeTiled costs about a microsecond
   struct TmapEntry {

@@ -258,7 +258,7 @@ int64_t ec_pipeline_launch_count(const ec_pipeline *p);
 /* Name of the kernel variant the last ec_dgemm* on this pipeline dispatched to. */
 const char *ec_pipeline_last_kernel(const ec_pipeline *p);
 /* Planning query; needs no device.  Which CTA tile configuration (1 = 128x128, 2 = 64x64,
- * 3 = 64x32, 4 = 32x32) and schedule (*stream_k 0 = whole tiles per CTA, 1 = stream-K) the
+ * 3 = 64x32, 4 = 32x32, 5 = 128x16) and schedule (*stream_k 0 = whole tiles per CTA, 1 = stream-K) the
  * dispatcher's cost model picks for `batch` products of m x n x k on a device with `sm_count`
  * SMs.  Honours the EC_FORCE_TILE / EC_STREAM_K overrides like the dispatcher itself. */
 int ec_plan_dgemm(int sm_count, int64_t m, int64_t n, int64_t k, int64_t batch, int *tile,

@@ -206,14 +206,14 @@ def test_dgemm_simt_kernel_odd_shapes(pipe, ta, tb, shape):
     assert orc.rel_frobenius(got, want) <= TOL
 
 
-@pytest.mark.parametrize("tile", [1, 2, 3, 4])
+@pytest.mark.parametrize("tile", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
 def test_every_tile_configuration(pipe, tile, ta, tb, monkeypatch):
-    """The four CTA tile shapes (128x128, 64x64, 64x32, 32x32) compute the same product."""
+    """The five CTA tile shapes (128x128, 64x64, 64x32, 32x32, 128x16) compute the same product."""
     monkeypatch.setenv("EC_FORCE_TILE", str(tile))
     for (m, n, k) in [(256, 192, 144), (130, 70, 50), (520, 264, 1030)]:
         got, want = run_dgemm(pipe, ta, tb, m, n, k, 1.25, -0.5, seed=tile + m)
-        suffix = {1: "", 2: "_s", 3: "_xs", 4: "_t"}[tile]
+        suffix = {1: "", 2: "_s", 3: "_xs", 4: "_t", 5: "_n"}[tile]
         name = "tma_dmma_" + ("T" if ta else "N") + ("T" if tb else "N") + suffix
         assert pipe.last_kernel() in (name, name + "_sk")
         assert orc.rel_frobenius(got, want) <= TOL
@@ -287,7 +287,7 @@ def test_slot_release_race_regression(pipe, monkeypatch):
     want = run(1)
     F = orc.fill_uniform(orc.SEED, 0, (n, n))
     assert orc.rel_frobenius(want[:, :n], orc.cpu_product(orc.fill_uniform(orc.SEED, 1, (n, n)), F)) <= TOL
-    for tile in (2, 3, 4):
+    for tile in (2, 3, 4, 5):
         for _ in range(4):
             assert np.array_equal(run(tile), want), f"tile configuration {tile} diverged"
 

@@ -25,7 +25,7 @@ def timed(fn, reps=20):
     return tot / reps
 
 # (m, n, k): C(m x n) = A(m x k) * B(k x n), column-major
-shapes = [(1 << 20, 32, 32), (1 << 20, 64, 64), (1 << 19, 128, 128), (1 << 20, 16, 128), (1 << 20, 128, 16),
+shapes = [(1 << 20, 32, 32), (1 << 20, 64, 64), (1 << 19, 128, 128), (1 << 20, 16, 128), (1 << 20, 16, 64), (1 << 21, 8, 128), (1 << 20, 128, 16),
           (64, 64, 1 << 20), (128, 128, 1 << 19), (8192, 8192, 64), (8192, 8192, 128)]
 for (m, n, k) in shapes:
     A = torch.randn(m * k, dtype=torch.float64, device=dev)
@@ -33,11 +33,11 @@ for (m, n, k) in shapes:
     C = torch.empty(m * n, dtype=torch.float64, device=dev)
     bytes_ = 8.0 * (m * k + k * n + m * n); flop = 2.0 * m * n * k
     row = []
-    for tile in (0, 1, 2, 3, 4):
+    for tile in (0, 1, 2, 3, 4, 5):
         if tile: os.environ["EC_FORCE_TILE"] = str(tile)
         else: os.environ.pop("EC_FORCE_TILE", None)
         ms = timed(lambda: pipe.dgemm(0, 0, m, n, k, 1.0, A.data_ptr(), m, B.data_ptr(), k, 0.0, C.data_ptr(), m))
-        row.append(f"{'auto' if not tile else 'LSXT'[tile - 1]}: {bytes_ / ms / 1e6:6.0f} GB/s {flop / ms / 1e9:5.1f} TF ({pipe.last_kernel().replace('tma_dmma_NN', '') or 'L'})")
+        row.append(f"{'auto' if not tile else 'LSXTN'[tile - 1]}: {bytes_ / ms / 1e6:6.0f} GB/s {flop / ms / 1e9:5.1f} TF ({pipe.last_kernel().replace('tma_dmma_NN', '') or 'L'})")
     os.environ.pop("EC_FORCE_TILE", None)
     # cuBLAS through torch: row-major views of the same column-major data: C^T = B^T A^T
     At = A.view(k, m); Bt = B.view(n, k); Ct = C.view(n, m)
