@@ -271,13 +271,17 @@ def e2e_legs(args, ec, orc, pipe, torch, dev, world, Fh):
         note = (f"e2e tensor reduced to {total} matrices: 2 x {total * mbytes / 2**30:.1f} GiB of pinned host memory "
                 f"is 60 % of MemAvailable ({avail / 2**30:.0f} GiB)")
         per_gpu = total // world
-    link = ec.host_link_probe(devices, 256 << 20, 5)
+    # Which GPUs to stream through is the scheduler's choice (devices = "auto"): the host side of
+    # the links is not uniform, and on this pool's 8-GPU boxes all eight together move less than
+    # the four with the wider host path alone (profiles/r02_link_probe.txt).  Both are measured:
+    # every GPU of the job (e2e_all_gpus) and the scheduler's pick (e2e, the headline).
+    picked, _, _ = ec.pick_stream_devices(devices) if world > 1 else (devices, 0.0, 0.0)
 
-    def call(in_ptrs, out_ptrs, count):
+    def call(in_ptrs, out_ptrs, count, devs):
         if world == 1:
             pipe.tensor_stream_raw(ec.EC_STREAM_RIGHT, Fh.ctypes.data, n, n, in_ptrs, out_ptrs, count, n, n)
         else:
-            pipe.tensor_stream_raw_multi(devices, ec.EC_STREAM_RIGHT, Fh.ctypes.data, n, n, in_ptrs, out_ptrs,
+            pipe.tensor_stream_raw_multi(devs, ec.EC_STREAM_RIGHT, Fh.ctypes.data, n, n, in_ptrs, out_ptrs,
                                          count, n, n)
 
     def check(out_col, gid, what):
@@ -301,31 +305,48 @@ def e2e_legs(args, ec, orc, pipe, torch, dev, world, Fh):
     out_ptrs = (C.c_void_p * total)(*[pin_out.ptr + mbytes * i for i in range(total)])
     pipe.set_stream_config(args.chunk, args.ring, 0)
     esteps = args.e2e_steps or min(args.steps, 5)
-    for _ in range(2):
-        call(in_ptrs, out_ptrs, total)       # warm-up: engine rings, child pipelines, NCCL communicators
-    l0 = pipe.launch_count()
-    t0 = time.perf_counter()
-    for _ in range(esteps):
-        call(in_ptrs, out_ptrs, total)       # returns with every result in host memory
-    dt = time.perf_counter() - t0
-    launches = pipe.launch_count() - l0
-    for i in (0, total // 3, total - 1):     # first shard, a middle one, the last matrix of the last shard
-        check(pin_out.array[:, i], i + 1, "e2e (pinned)")
-    rate = total * esteps / dt
-    gbs = total * mbytes * esteps / dt / 1e9
-    e2e = {"value": rate, "unit": "matrices/s", "h2d_bytes_per_step": total * mbytes, "d2h_bytes_per_step": total * mbytes,
-           "steps": esteps, "matrices_per_gpu": per_gpu, "matrices_total": total, "ms_per_step": 1e3 * dt / esteps,
-           "host_memory": "pinned (cudaHostAlloc), DMA'd in place",
-           "api": ("ec_tensor_stream_run (CudaPipeline::right_multiply)" if world == 1 else
-                   f"ec_tensor_stream_run_multi over {world} GPUs (CudaPipeline::right_multiply(tensor, A, devices)): one call, "
-                   f"one process, one worker thread + ring per GPU, NCCL broadcast of F inside the timed region"),
-           "tflops": rate * 2.0 * n ** 3 / 1e12, "gpu_launches_per_step": launches / esteps,
-           "link_gbs_each_way": gbs, "link_gbs_each_way_per_gpu": gbs / world,
-           "link_roofline_gbs": {"h2d_only": link["h2d"], "d2h_only": link["d2h"],
-                                 "bidirectional_each_way": link["bidir_each_way"],
-                                 "how": f"plain pinned cudaMemcpyAsync, 256 MiB per copy, on all {world} GPU(s) at once, best of 5, "
-                                        f"measured in this run just before the leg; GB/s summed over the GPUs"},
-           "frac_of_link": gbs / link["bidir_each_way"] if link["bidir_each_way"] else None}
+
+    def pinned_leg(devs):
+        link = ec.host_link_probe(devs, 256 << 20, 5)
+        pin_out.array[:, :] = 0.0
+        for _ in range(2):
+            call(in_ptrs, out_ptrs, total, devs)   # warm-up: engine rings, child pipelines, NCCL communicators
+        l0 = pipe.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            call(in_ptrs, out_ptrs, total, devs)   # returns with every result in host memory
+        dt = time.perf_counter() - t0
+        launches = pipe.launch_count() - l0
+        for i in (0, total // 3, total - 1):       # first shard, a middle one, the last matrix of the last shard
+            check(pin_out.array[:, i], i + 1, "e2e (pinned)")
+        rate = total * esteps / dt
+        gbs = total * mbytes * esteps / dt / 1e9
+        g = len(devs)
+        return {"value": rate, "unit": "matrices/s", "h2d_bytes_per_step": total * mbytes,
+                "d2h_bytes_per_step": total * mbytes, "steps": esteps, "matrices_total": total,
+                "matrices_per_gpu": total // g, "gpus_streaming": g, "devices": list(devs),
+                "ms_per_step": 1e3 * dt / esteps, "host_memory": "pinned (cudaHostAlloc), DMA'd in place",
+                "api": ("ec_tensor_stream_run (CudaPipeline::right_multiply)" if world == 1 else
+                        f"ec_tensor_stream_run_multi over {g} GPUs (CudaPipeline::right_multiply(tensor, A, devices)): one "
+                        f"call, one process, one worker thread + ring per GPU, NCCL broadcast of F inside the timed region"),
+                "tflops": rate * 2.0 * n ** 3 / 1e12, "gpu_launches_per_step": launches / esteps,
+                "link_gbs_each_way": gbs, "link_gbs_each_way_per_gpu": gbs / g,
+                "link_roofline_gbs": {"h2d_only": link["h2d"], "d2h_only": link["d2h"],
+                                      "bidirectional_each_way": link["bidir_each_way"],
+                                      "how": f"plain pinned cudaMemcpyAsync, 256 MiB per copy, on these {g} GPU(s) at once, best "
+                                             f"of 5, measured in this run just before the leg; GB/s summed over the GPUs"},
+                "frac_of_link": gbs / link["bidir_each_way"] if link["bidir_each_way"] else None}
+
+    e2e_all = pinned_leg(devices)
+    if list(picked) != list(devices):
+        e2e = pinned_leg(list(picked))
+        e2e["device_selection"] = (f"auto (ec_pick_stream_devices): GPUs {list(picked)} of {world} -- by measurement the host "
+                                   f"moves more through these alone than through all {world} at once")
+        e2e["all_gpus"] = e2e_all
+    else:
+        e2e = e2e_all
+        if world > 1:
+            e2e["device_selection"] = f"auto (ec_pick_stream_devices) kept all {world} GPUs"
     if note:
         e2e["note"] = note
 
@@ -338,11 +359,11 @@ def e2e_legs(args, ec, orc, pipe, torch, dev, world, Fh):
     outs = np.zeros((elems, ptotal), dtype=np.float64, order="F")      # touched: no page faults in the timed region
     ipp = (C.c_void_p * ptotal)(*[base.ctypes.data + mbytes * i for i in range(ptotal)])
     opp = (C.c_void_p * ptotal)(*[outs.ctypes.data + mbytes * i for i in range(ptotal)])
-    call(ipp, opp, ptotal)
+    call(ipp, opp, ptotal, list(picked))
     psteps = max(2, min(esteps, 3))
     t0 = time.perf_counter()
     for _ in range(psteps):
-        call(ipp, opp, ptotal)
+        call(ipp, opp, ptotal, list(picked))
     dt = time.perf_counter() - t0
     for i in (0, ptotal - 1):
         check(outs[:, i], i + 1, "e2e (pageable)")
@@ -352,6 +373,7 @@ def e2e_legs(args, ec, orc, pipe, torch, dev, world, Fh):
                     "ms_per_step": 1e3 * dt / psteps,
                     "host_memory": "pageable (numpy heap memory), staged through the engines' pinned rings by worker threads",
                     "host_gbs_each_way": ptotal * mbytes * psteps / dt / 1e9, "host_threads": len(os.sched_getaffinity(0)),
+                    "devices": list(picked),
                     "what": "the same one call on the memory the reference arm runs from: separates 'API + overlap' "
                             "(this figure / reference) from 'caller pins its matrices' (e2e / reference)"}
     pipe.set_stream_config(0, 0, 0)

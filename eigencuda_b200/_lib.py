@@ -15,6 +15,7 @@ EC_OK, EC_ERR_SHAPE, EC_ERR_NOMEM, EC_ERR_COPY, EC_ERR_CUDA, EC_ERR_ARG, EC_ERR_
 EC_OP_N, EC_OP_T = 0, 1
 EC_BACKEND_FP64_DMMA, EC_BACKEND_OZAKI_I8 = 0, 1
 EC_STREAM_RIGHT, EC_STREAM_LEFT, EC_STREAM_LEFT_T, EC_STREAM_BASIS = 0, 1, 2, 3
+EC_DEVICES_AUTO = -1
 
 _vp, _i64, _int, _dbl, _u64 = C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_uint64
 _dp = C.c_void_p  # device / host double* passed as raw addresses
@@ -67,6 +68,7 @@ SIGNATURES = {
     "ec_dgemm_2d": (_int, [_vp, _vp, _vp, _vp, _i64, C.POINTER(_dbl)]),
     "ec_dgemm_2d_host": (_int, [C.POINTER(_int), _int, _i64, _i64, _i64, _dp, _i64, _dp, _i64, _dp, _i64]),
     "ec_plan_chunks": (_i64, [_i64, _i64, _int, C.POINTER(_i64), _i64]),
+    "ec_pick_stream_devices": (_int, [C.POINTER(_int), _int, C.POINTER(_int), C.POINTER(_int), C.POINTER(_dbl)]),
     "ec_plan_shard": (_int, [_i64, _int, _int, C.POINTER(_i64), C.POINTER(_i64)]),
     "ec_host_link_probe": (_int, [C.POINTER(_int), _int, C.c_size_t, _int, C.POINTER(_dbl)]),
     "ec_tensor_stream_run_device": (_int, [_vp, _int, _dp, _i64, _i64, _dp, _dp, _i64, _i64, _i64]),

@@ -369,8 +369,10 @@ def dgemm_2d(A, B, devices="all"):
 def _device_list(devices):
     """("all" | iterable of device indices) -> (ctypes int array or None, ndev); ndev 0 = every device."""
     if isinstance(devices, str):
+        if devices == "auto":
+            return None, _lib.EC_DEVICES_AUTO
         if devices != "all":
-            raise ValueError('devices must be a list of device indices or "all"')
+            raise ValueError('devices must be a list of device indices, "all" or "auto"')
         return None, 0
     devs = [int(d) for d in devices]
     if not devs:
@@ -393,6 +395,16 @@ def plan_chunks(count, chunk, ramp=True):
     buf = (C.c_int64 * n)()
     lib.ec_plan_chunks(int(count), int(chunk), int(bool(ramp)), buf, n)
     return list(buf)
+
+
+def pick_stream_devices(devices="all"):
+    """The subset of `devices` the host streams through fastest, by measurement
+    (ec_pick_stream_devices).  Returns (device list, GB/s each way of that set, GB/s of all)."""
+    dev_arr, ndev = _device_list(devices)
+    cap = ndev if ndev > 0 else max(1, count_available_gpus())
+    out, nout, gbs = (C.c_int * cap)(), C.c_int(), (C.c_double * 2)()
+    check(lib.ec_pick_stream_devices(dev_arr, max(ndev, 0), out, C.byref(nout), gbs))
+    return list(out[: nout.value]), gbs[0], gbs[1]
 
 
 def host_link_probe(devices="all", nbytes=256 << 20, reps=5):

@@ -631,6 +631,22 @@ int ec_plan_shard(int64_t count, int ndev, int idx, int64_t *lo, int64_t *hi) {
   return EC_OK;
 }
 
+int ec_pick_stream_devices(const int *devices, int ndev, int *out_devices, int *out_ndev, double *out_gbs) {
+  if (!out_devices || !out_ndev) return fail(EC_ERR_ARG, "null out pointer");
+  std::vector<int> devs;
+  int rc = device_list_or_all(devices, ndev, &devs);
+  if (rc) return rc;
+  DevicePick pick;
+  if ((rc = pick_stream_devices_impl(devs, &pick))) return rc;
+  for (size_t i = 0; i < pick.picked.size(); ++i) out_devices[i] = pick.picked[i];
+  *out_ndev = (int)pick.picked.size();
+  if (out_gbs) {
+    out_gbs[0] = pick.gbs_picked;
+    out_gbs[1] = pick.gbs_all;
+  }
+  return EC_OK;
+}
+
 int ec_host_link_probe(const int *devices, int ndev, size_t bytes, int reps, double *out_gbs) {
   return host_link_probe_impl(devices, ndev, bytes, reps, out_gbs);
 }

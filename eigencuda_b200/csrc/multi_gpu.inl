@@ -207,6 +207,13 @@ struct MultiGpu {
 
 namespace {
 
+struct DevicePick {
+  std::vector<int> from, picked;
+  double gbs_picked = 0.0, gbs_all = 0.0;
+};
+int pick_stream_devices_impl(const std::vector<int> &devs, DevicePick *out);
+int device_list_or_all(const int *devices, int ndev, std::vector<int> *devs);
+
 // Balanced, contiguous, order-preserving partition of range(count) over `parts` workers
 // (the same rule as eigencuda_b200/shard.py: shard_range).
 inline void shard_range(int64_t count, int parts, int idx, int64_t *lo, int64_t *hi) {
@@ -218,7 +225,7 @@ int tensor_stream_run_multi_impl(ec_pipeline *p, const int *devices, int ndev, i
                                  int64_t f_rows, int64_t f_cols, const double *const *tensor,
                                  double *const *results, int64_t count, int64_t t_rows, int64_t t_cols) {
   if (!p) return fail(EC_ERR_ARG, "null pipeline");
-  if (ndev < 0 || (ndev > 0 && !devices)) return fail(EC_ERR_ARG, "bad device list");
+  if (ndev < EC_DEVICES_AUTO || (ndev > 0 && !devices)) return fail(EC_ERR_ARG, "bad device list");
   if (count < 0 || f_rows < 0 || f_cols < 0 || t_rows < 0 || t_cols < 0)
     return fail(EC_ERR_ARG, "negative size");
   StreamShape sh;
@@ -227,12 +234,11 @@ int tensor_stream_run_multi_impl(ec_pipeline *p, const int *devices, int ndev, i
   if (count == 0) return EC_OK;
   if (!F || !tensor || !results) return fail(EC_ERR_ARG, "null pointer");
   std::vector<int> devs;
-  if (ndev == 0) {   // every device of the box
-    const int all = (int)ec_device_count();
-    for (int d = 0; d < all; ++d) devs.push_back(d);
-    if (devs.empty()) return fail(EC_ERR_CUDA, "no CUDA device visible");
-  } else {
-    devs.assign(devices, devices + ndev);
+  if ((rc = device_list_or_all(devices, std::max(ndev, 0), &devs))) return rc;
+  if (ndev == EC_DEVICES_AUTO) {   // the subset of the box's devices that streams fastest, by measurement
+    DevicePick pick;
+    if ((rc = pick_stream_devices_impl(devs, &pick))) return rc;
+    devs = pick.picked;
   }
   const int64_t f_sz = f_rows * f_cols;
   if (t_rows * t_cols == 0 || sh.r_rows * sh.r_cols == 0 || f_sz == 0)   // degenerate: handled on the host
@@ -332,80 +338,172 @@ int tensor_stream_run_multi_impl(ec_pipeline *p, const int *devices, int ndev, i
 // ------------------------------------------------------------------------------------------
 namespace {
 
-int host_link_probe_impl(const int *devices, int ndev, size_t bytes, int reps, double *out_gbs) {
-  if (!out_gbs) return fail(EC_ERR_ARG, "null out pointer");
-  out_gbs[0] = out_gbs[1] = out_gbs[2] = 0.0;
-  if (ndev < 0 || (ndev > 0 && !devices) || bytes == 0 || reps <= 0) return fail(EC_ERR_ARG, "bad probe arguments");
-  std::vector<int> devs;
-  if (ndev == 0)
-    for (int d = 0; d < (int)ec_device_count(); ++d) devs.push_back(d);
-  else
-    devs.assign(devices, devices + ndev);
-  if (devs.empty()) return fail(EC_ERR_CUDA, "no CUDA device visible");
-  const int G = (int)devs.size();
+// Buffers and streams for plain pinned copies on a set of devices; run() times one mode on a subset.
+struct LinkProbe {
   struct Dev {
+    int device = -1;
     void *d_in = nullptr, *d_out = nullptr, *h_in = nullptr, *h_out = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;
   };
-  std::vector<Dev> D(G);
+  std::vector<Dev> D;
+  size_t bytes = 0;
   int prev = 0;
-  cudaGetDevice(&prev);
-  int rc = EC_OK;
-  auto cleanup = [&] {
-    for (int g = 0; g < G; ++g) {
-      cudaSetDevice(devs[g]);
-      if (D[g].s_in) cudaStreamDestroy(D[g].s_in);
-      if (D[g].s_out) cudaStreamDestroy(D[g].s_out);
-      if (D[g].d_in) cudaFree(D[g].d_in);
-      if (D[g].d_out) cudaFree(D[g].d_out);
-      if (D[g].h_in) cudaFreeHost(D[g].h_in);
-      if (D[g].h_out) cudaFreeHost(D[g].h_out);
+
+  int setup(const std::vector<int> &devs, size_t bytes_) {
+    bytes = bytes_;
+    cudaGetDevice(&prev);
+    D.resize(devs.size());
+    for (size_t g = 0; g < devs.size(); ++g) {
+      D[g].device = devs[g];
+      EC_CUDA(cudaSetDevice(devs[g]));
+      EC_CUDA(cudaMalloc(&D[g].d_in, bytes));
+      EC_CUDA(cudaMalloc(&D[g].d_out, bytes));
+      EC_CUDA(cudaHostAlloc(&D[g].h_in, bytes, cudaHostAllocPortable));
+      EC_CUDA(cudaHostAlloc(&D[g].h_out, bytes, cudaHostAllocPortable));
+      std::memset(D[g].h_in, 1, bytes);
+      std::memset(D[g].h_out, 0, bytes);
+      EC_CUDA(cudaMemsetAsync(D[g].d_out, 0, bytes, 0));
+      EC_CUDA(cudaStreamCreateWithFlags(&D[g].s_in, cudaStreamNonBlocking));
+      EC_CUDA(cudaStreamCreateWithFlags(&D[g].s_out, cudaStreamNonBlocking));
+      EC_CUDA(cudaDeviceSynchronize());
     }
-    cudaSetDevice(prev);
-  };
-#define PROBE_CUDA(call)                                                                          \
-  do {                                                                                            \
-    cudaError_t _e = (call);                                                                      \
-    if (_e != cudaSuccess) {                                                                      \
-      rc = fail(EC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
-      cleanup();                                                                                  \
-      return rc;                                                                                  \
-    }                                                                                             \
-  } while (0)
-  for (int g = 0; g < G; ++g) {
-    PROBE_CUDA(cudaSetDevice(devs[g]));
-    PROBE_CUDA(cudaMalloc(&D[g].d_in, bytes));
-    PROBE_CUDA(cudaMalloc(&D[g].d_out, bytes));
-    PROBE_CUDA(cudaHostAlloc(&D[g].h_in, bytes, cudaHostAllocPortable));
-    PROBE_CUDA(cudaHostAlloc(&D[g].h_out, bytes, cudaHostAllocPortable));
-    std::memset(D[g].h_in, 1, bytes);
-    std::memset(D[g].h_out, 0, bytes);
-    PROBE_CUDA(cudaMemsetAsync(D[g].d_out, 0, bytes, 0));
-    PROBE_CUDA(cudaStreamCreateWithFlags(&D[g].s_in, cudaStreamNonBlocking));
-    PROBE_CUDA(cudaStreamCreateWithFlags(&D[g].s_out, cudaStreamNonBlocking));
-    PROBE_CUDA(cudaDeviceSynchronize());
+    return EC_OK;
   }
-  constexpr int INNER = 2;   // copies per direction per device per timed repetition
-  for (int mode = 0; mode < 3; ++mode) {   // 0: H2D only, 1: D2H only, 2: both at once
+  // mode 0: H2D only, 1: D2H only, 2: both at once.  `use[g]` selects the devices that take part.
+  // Result: GB/s in each direction, summed over the participating devices, best of `reps`
+  // (after one warm-up repetition).
+  int run(int mode, const std::vector<char> &use, int reps, double *gbs) {
+    constexpr int INNER = 2;   // copies per direction per device per timed repetition
     double best = 1e300;
-    for (int rep = 0; rep < reps + 1; ++rep) {   // first repetition is a warm-up
+    int active = 0;
+    for (size_t g = 0; g < D.size(); ++g) active += use[g] ? 1 : 0;
+    for (int rep = 0; rep < reps + 1; ++rep) {
       const auto t0 = std::chrono::steady_clock::now();
       for (int it = 0; it < INNER; ++it)
-        for (int g = 0; g < G; ++g) {
-          if (mode != 1) PROBE_CUDA(cudaMemcpyAsync(D[g].d_in, D[g].h_in, bytes, cudaMemcpyHostToDevice, D[g].s_in));
-          if (mode != 0) PROBE_CUDA(cudaMemcpyAsync(D[g].h_out, D[g].d_out, bytes, cudaMemcpyDeviceToHost, D[g].s_out));
+        for (size_t g = 0; g < D.size(); ++g) {
+          if (!use[g]) continue;
+          if (mode != 1) EC_CUDA(cudaMemcpyAsync(D[g].d_in, D[g].h_in, bytes, cudaMemcpyHostToDevice, D[g].s_in));
+          if (mode != 0) EC_CUDA(cudaMemcpyAsync(D[g].h_out, D[g].d_out, bytes, cudaMemcpyDeviceToHost, D[g].s_out));
         }
-      for (int g = 0; g < G; ++g) {
-        PROBE_CUDA(cudaStreamSynchronize(D[g].s_in));
-        PROBE_CUDA(cudaStreamSynchronize(D[g].s_out));
+      for (size_t g = 0; g < D.size(); ++g) {
+        if (!use[g]) continue;
+        EC_CUDA(cudaStreamSynchronize(D[g].s_in));
+        EC_CUDA(cudaStreamSynchronize(D[g].s_out));
       }
       const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       if (rep > 0) best = std::min(best, dt);
     }
-    out_gbs[mode] = (double)G * INNER * (double)bytes / best / 1e9;   // each way, summed over the devices
+    *gbs = (double)active * INNER * (double)bytes / best / 1e9;
+    return EC_OK;
   }
-#undef PROBE_CUDA
-  cleanup();
+  ~LinkProbe() {
+    for (Dev &d : D) {
+      if (d.device < 0) continue;
+      cudaSetDevice(d.device);
+      if (d.s_in) cudaStreamDestroy(d.s_in);
+      if (d.s_out) cudaStreamDestroy(d.s_out);
+      if (d.d_in) cudaFree(d.d_in);
+      if (d.d_out) cudaFree(d.d_out);
+      if (d.h_in) cudaFreeHost(d.h_in);
+      if (d.h_out) cudaFreeHost(d.h_out);
+    }
+    cudaSetDevice(prev);
+  }
+};
+
+int device_list_or_all(const int *devices, int ndev, std::vector<int> *devs) {
+  if (ndev < 0 || (ndev > 0 && !devices)) return fail(EC_ERR_ARG, "bad device list");
+  if (ndev == 0)
+    for (int d = 0; d < (int)ec_device_count(); ++d) devs->push_back(d);
+  else
+    devs->assign(devices, devices + ndev);
+  if (devs->empty()) return fail(EC_ERR_CUDA, "no CUDA device visible");
+  return EC_OK;
+}
+
+int host_link_probe_impl(const int *devices, int ndev, size_t bytes, int reps, double *out_gbs) {
+  if (!out_gbs) return fail(EC_ERR_ARG, "null out pointer");
+  out_gbs[0] = out_gbs[1] = out_gbs[2] = 0.0;
+  if (bytes == 0 || reps <= 0) return fail(EC_ERR_ARG, "bad probe arguments");
+  std::vector<int> devs;
+  int rc = device_list_or_all(devices, ndev, &devs);
+  if (rc) return rc;
+  LinkProbe P;
+  if ((rc = P.setup(devs, bytes))) return rc;
+  const std::vector<char> all(devs.size(), 1);
+  for (int mode = 0; mode < 3; ++mode)
+    if ((rc = P.run(mode, all, reps, &out_gbs[mode]))) return rc;
+  return EC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Which of the box's GPUs to stream through.  The streamed job is bound by the HOST side of the
+// links, and that side is not uniform: on this pool's 8-GPU boxes GPUs 0-3 hang off a path that
+// gives 51 GB/s each way however many of them transfer, GPUs 4-7 off one that gives 95, and all
+// eight together reach only 64 -- the narrow half drags the wide half down
+// (profiles/r02_link_probe.txt).  More GPUs is then less throughput.  The choice is made by
+// measurement, once per process and device list: bidirectional pinned copies (64 MiB) on all
+// devices, on each pair of neighbours, then greedily on unions of pairs from the fastest down,
+// keeping a pair only if the aggregate grows by more than 5 %.
+// ------------------------------------------------------------------------------------------
+std::mutex g_pick_mu;
+std::vector<DevicePick> g_picks;
+
+int pick_stream_devices_impl(const std::vector<int> &devs, DevicePick *out) {
+  {
+    std::lock_guard<std::mutex> lk(g_pick_mu);
+    for (const DevicePick &p : g_picks)
+      if (p.from == devs) {
+        *out = p;
+        return EC_OK;
+      }
+  }
+  DevicePick pick;
+  pick.from = devs;
+  const int n = (int)devs.size();
+  LinkProbe P;
+  int rc = P.setup(devs, (size_t)64 << 20);
+  if (rc) return rc;
+  std::vector<char> use(n, 1);
+  if ((rc = P.run(2, use, 2, &pick.gbs_all))) return rc;
+  pick.picked = devs;
+  pick.gbs_picked = pick.gbs_all;
+  if (n > 2) {
+    struct Group { int lo, hi; double gbs; };
+    std::vector<Group> groups;
+    for (int lo = 0; lo < n; lo += 2) {
+      Group g{lo, std::min(lo + 2, n), 0.0};
+      std::fill(use.begin(), use.end(), 0);
+      for (int i = g.lo; i < g.hi; ++i) use[i] = 1;
+      if ((rc = P.run(2, use, 2, &g.gbs))) return rc;
+      groups.push_back(g);
+    }
+    std::sort(groups.begin(), groups.end(), [](const Group &a, const Group &b) { return a.gbs > b.gbs; });
+    std::vector<char> best(n, 0);
+    for (int i = groups[0].lo; i < groups[0].hi; ++i) best[i] = 1;
+    double best_gbs = groups[0].gbs;
+    for (size_t k = 1; k < groups.size(); ++k) {
+      std::vector<char> trial = best;
+      for (int i = groups[k].lo; i < groups[k].hi; ++i) trial[i] = 1;
+      double gbs = 0.0;
+      if ((rc = P.run(2, trial, 2, &gbs))) return rc;
+      if (gbs > 1.05 * best_gbs) {
+        best = trial;
+        best_gbs = gbs;
+      }
+    }
+    if (best_gbs > 1.05 * pick.gbs_all) {   // otherwise: every device (more GEMM capacity, same link)
+      pick.picked.clear();
+      for (int i = 0; i < n; ++i)
+        if (best[i]) pick.picked.push_back(devs[i]);
+      pick.gbs_picked = best_gbs;
+    }
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_pick_mu);
+    g_picks.push_back(pick);
+  }
+  *out = pick;
   return EC_OK;
 }
 

@@ -91,6 +91,17 @@ class CudaPipeline {
   // and broadcast with NCCL over NVLink; every device writes its results straight into
   // results[i].  The pipeline's own device need not be in the list.
   // ---------------------------------------------------------------------------------------
+  // The GPUs of the box the host streams through fastest, chosen by measurement once per process
+  // (ec_pick_stream_devices): the host side of the links is not uniform, and more GPUs can be
+  // less throughput for this transfer-bound job.  Pass the result as `devices`.
+  static std::vector<int> auto_devices() {
+    std::vector<int> out(static_cast<size_t>(ec_device_count() > 0 ? ec_device_count() : 1));
+    int n = 0;
+    detail::throw_on_error(ec_pick_stream_devices(nullptr, 0, out.data(), &n, nullptr));
+    out.resize(static_cast<size_t>(n));
+    return out;
+  }
+
   std::vector<Eigen::MatrixXd> right_multiply(const std::vector<Eigen::MatrixXd> &tensor,
                                               const Eigen::MatrixXd &A,
                                               const std::vector<int> &devices) const {

@@ -153,12 +153,25 @@ int ec_tensor_stream_run_device(ec_pipeline *p, int kind, const double *F_dev, i
  * streams; F goes to devices[0] once and is broadcast to the others with NCCL over NVLink
  * (libnccl.so.2 is bound at run time: EC_ERR_UNSUPPORTED when ndev > 1 and it cannot be loaded);
  * every device DMAs its results straight into results[i]; no result exchange.  ndev == 0 means
- * every device of the box (devices may then be NULL).  `p` carries the engine knobs and the
+ * every device of the box (devices may then be NULL), ndev == EC_DEVICES_AUTO the subset of them
+ * the host streams through fastest (ec_pick_stream_devices).  `p` carries the engine knobs and the
  * backend and owns the per-device state, which is kept across calls.  The reference has no
  * multi-GPU path; this replaces its unused count_available_gpus(), src/cudamatrix.cc:14-18. */
 int ec_tensor_stream_run_multi(ec_pipeline *p, const int *devices, int ndev, int kind, const double *F,
                                int64_t f_rows, int64_t f_cols, const double *const *tensor,
                                double *const *results, int64_t count, int64_t t_rows, int64_t t_cols);
+/* ndev value for ec_tensor_stream_run_multi: stream through the subset of the box's devices that
+ * the host moves data to and from fastest, chosen by measurement (ec_pick_stream_devices). */
+enum { EC_DEVICES_AUTO = -1 };
+/* The streamed job is bound by the host side of the GPU links, which is not uniform across the
+ * GPUs of a box (on this pool's 8-GPU boxes all eight together move LESS than GPUs 4-7 alone:
+ * profiles/r02_link_probe.txt).  Measures bidirectional pinned-copy bandwidth on all listed
+ * devices (ndev == 0: every device), on pairs of neighbours and on unions of pairs, and returns
+ * the subset with the highest aggregate (every device unless a subset is more than 5 % faster).
+ * out_devices must hold ndev (or ec_device_count()) entries; out_gbs (optional): [0] = GB/s each
+ * way of the chosen set, [1] = of all devices.  Costs about a second the first time, cached per
+ * process and device list afterwards. */
+int ec_pick_stream_devices(const int *devices, int ndev, int *out_devices, int *out_ndev, double *out_gbs);
 /* Planning query; needs no device: the index range [*lo, *hi) of a `count`-element tensor that
  * device number idx of ndev takes in ec_tensor_stream_run_multi. */
 int ec_plan_shard(int64_t count, int ndev, int idx, int64_t *lo, int64_t *hi);

@@ -132,6 +132,11 @@ int main() {
   {   // an empty list means every device of the box
     known_answers(std::vector<int>());
   }
+  {   // the scheduler's own pick of devices (by host-link measurement)
+    const std::vector<int> picked = ecu::CudaPipeline::auto_devices();
+    EXPECT(!picked.empty() && static_cast<int>(picked.size()) <= available);
+    known_answers(picked);
+  }
   if (available >= 2) {   // the pipeline's own device need not lead the list
     std::vector<int> devices = {1, 0};
     sharded_equals_single(devices);

@@ -526,6 +526,7 @@ def _device_sets():
     if g >= 2:
         sets.append([1, 0])
     sets.append("all")
+    sets.append("auto")
     return sets
 
 
@@ -684,6 +685,16 @@ def test_dgemm_2d_generated_operands_and_shape_errors():
     A, B = rnd(21, (200, 300)), rnd(22, (300, 100))
     assert orc.rel_frobenius(ec.dgemm_2d(A, B), orc.dgemm(A, B, flavour="ld")) <= TOL
     grid.close()
+
+
+def test_pick_stream_devices_returns_a_measured_subset():
+    g = ec.count_available_gpus()
+    picked, gbs_picked, gbs_all = ec.pick_stream_devices("all")
+    assert 1 <= len(picked) <= g and len(set(picked)) == len(picked) and all(0 <= d < g for d in picked)
+    assert gbs_picked >= gbs_all > 5.0
+    if len(picked) < g:
+        assert gbs_picked > 1.05 * gbs_all                 # a subset is only chosen when clearly faster
+    assert ec.pick_stream_devices("all")[0] == picked        # cached: the same answer, no second probe
 
 
 def test_host_link_probe_reports_a_ceiling():
