@@ -97,3 +97,36 @@ def test_cpp_headers_compile_against_the_abi(tmp_path):
         pytest.skip("CUDA headers not present")
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
+
+
+def test_cmake_package_builds_the_reference_test_and_is_findable(tmp_path):
+    """the CMake package.  Configure this project against the in-tree library
+    (EIGENCUDA_PREBUILT_LIB: no nvcc run), build `unit_test_dot` -- the reference's own test target name
+    (reference src/tests/CMakeLists.txt:3-17) -- install, then configure and build a separate caller
+    project that does find_package(eigencuda) and links the plain target name `eigencuda` as the
+    reference's callers do (reference src/CMakeLists.txt:2)."""
+    import shutil
+    import eigencuda_b200._lib as L
+    if not shutil.which("cmake") or not os.path.exists("/usr/local/cuda/include/cuda_runtime_api.h"):
+        pytest.skip("cmake or the CUDA headers are not present")
+    build, prefix, cbuild = tmp_path / "build", tmp_path / "prefix", tmp_path / "consumer_build"
+    run = lambda cmd: subprocess.run(cmd, capture_output=True, text=True)
+    res = run(["cmake", "-S", ROOT, "-B", str(build), "-DENABLE_TESTING=ON", f"-DEIGENCUDA_PREBUILT_LIB={L.LIB_PATH}",
+               "-DCUDAToolkit_ROOT=/usr/local/cuda"])
+    assert res.returncode == 0, res.stdout + res.stderr
+    res = run(["cmake", "--build", str(build), "--target", "unit_test_dot", "unit_test_multi_gpu", "-j", "4"])
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert (build / "unit_test_dot").exists() and (build / "unit_test_multi_gpu").exists()
+    res = run(["cmake", "--install", str(build), "--prefix", str(prefix)])
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert (prefix / "lib" / "cmake" / "eigencuda" / "eigencudaConfig.cmake").exists()
+    assert (prefix / "include" / "cudapipeline.hpp").exists() and (prefix / "lib" / "libeigencuda_b200.so").exists()
+    res = run(["cmake", "-S", os.path.join(ROOT, "tests", "cmake_consumer"), "-B", str(cbuild),
+               f"-DCMAKE_PREFIX_PATH={prefix}", "-DCUDAToolkit_ROOT=/usr/local/cuda",
+               f"-DEIGENCUDA_TEST_SOURCE={ROOT}/tests/cpp/test_dot_compat.cc",
+               f"-DEIGEN_STANDIN_DIR={ROOT}/oracle/eigen_standin"])
+    assert res.returncode == 0, res.stdout + res.stderr
+    res = run(["cmake", "--build", str(cbuild)])
+    assert res.returncode == 0, res.stdout + res.stderr
+    out = run(["ldd", str(cbuild / "consumer")]).stdout
+    assert "libeigencuda_b200.so" in out and "cublas" not in out.lower()
