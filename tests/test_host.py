@@ -202,7 +202,7 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
 # the dispatcher's cost model, queried without a device: the choices that were measured best on
 # a B200 (profiles/r01_small_probe.txt, r01_batched_small_probe.txt, r01_skinny_probe.txt) stay put
 # ---------------------------------------------------------------------------------------------
-L, S, XS, T = 1, 2, 3, 4
+L, S, XS, T, N16 = 1, 2, 3, 4, 5
 
 
 @pytest.mark.parametrize("shape,expected", [
@@ -220,7 +220,8 @@ L, S, XS, T = 1, 2, 3, 4
     ((128, 128, 128, 8192), (L, False)),
     ((64, 64, 1 << 20, 1), (S, True)),          # inner-product shape: stream-K over the whole grid
     ((1 << 20, 32, 32, 1), (XS, False)),        # tall and skinny: HBM-bound
-    ((1 << 20, 16, 128, 1), (XS, False)),
+    ((1 << 20, 16, 128, 1), (N16, False)),      # at most 16 columns: the 128x16 tile (no padded DMMAs)
+    ((1 << 21, 8, 64, 1), (N16, False)),
     ((1 << 20, 128, 16, 1), (L, False)),
 ])
 def test_cost_model_choices(shape, expected, monkeypatch):
