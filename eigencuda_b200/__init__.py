@@ -3,7 +3,7 @@ CudaMatrix operands, FP64, column-major).  See DESIGN.md.  Importing this packag
 in-tree CUDA library; it raises if that library has not been built (no CPU fallback)."""
 from ._lib import (EC_DEVICES_AUTO, EC_BACKEND_FP64_DMMA, EC_BACKEND_OZAKI_I8, EC_OP_N, EC_OP_T, EC_STREAM_BASIS,
                    EC_STREAM_LEFT, EC_STREAM_LEFT_T, EC_STREAM_RIGHT, EigenCudaError, LIB_PATH)
-from .api import (CudaMatrix, CudaPipeline, DeviceGrid, DistMatrix, Index, dgemm_2d, PinnedBuffer, count_available_gpus, host_link_probe, host_pin, pick_stream_devices, plan_chunks, plan_dgemm, plan_shard,
+from .api import (CudaMatrix, CudaPipeline, DeviceGrid, DistMatrix, Index, dgemm_2d, PinnedBuffer, count_available_gpus, debug_hold_sms, host_link_probe, host_pin, pick_stream_devices, plan_chunks, plan_dgemm, plan_shard,
                   result_shape)
 from .shard import broadcast_fixed, shard_range
 

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libeigencuda_b200.so")
+# EIGENCUDA_B200_LIB points the binding at another build of the same library (A/B measurements)
+LIB_PATH = os.environ.get("EIGENCUDA_B200_LIB") or os.path.join(_HERE, "lib", "libeigencuda_b200.so")
 
 EC_OK, EC_ERR_SHAPE, EC_ERR_NOMEM, EC_ERR_COPY, EC_ERR_CUDA, EC_ERR_ARG, EC_ERR_UNSUPPORTED = range(7)
 EC_OP_N, EC_OP_T = 0, 1
@@ -83,6 +84,8 @@ SIGNATURES = {
     "ec_fill_uniform": (_int, [_vp, _u64, _u64, _dp, _i64]),
     "ec_fill_uniform_batched": (_int, [_vp, _u64, _u64, _dp, _i64, _i64]),
     "ec_fill_uniform_block": (_int, [_vp, _u64, _u64, _dp, _i64, _i64, _i64, _i64, _i64, _i64]),
+    "ec_pipeline_contention_events": (_i64, [_vp]),
+    "ec_debug_hold_sms": (_int, [_int, _vp, _int, _i64]),
     "ec_pipeline_launch_count": (_i64, [_vp]),
     "ec_pipeline_last_kernel": (C.c_char_p, [_vp]),
 }
@@ -96,6 +99,8 @@ def load(path=LIB_PATH):
             "There is no CPU fallback.")
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
+        if os.environ.get("EIGENCUDA_B200_LIB") and not hasattr(lib, name):
+            continue             # an older build under A/B measurement: bind what it has
         fn = getattr(lib, name)  # AttributeError here = ABI drift, fail loudly
         fn.restype = res
         fn.argtypes = args

@@ -248,6 +248,10 @@ class CudaPipeline:
     def launch_count(self):
         return int(lib.ec_pipeline_launch_count(self._h))
 
+    def contention_events(self):
+        """How often the dispatcher found the GPU shared and switched to dynamic schedules."""
+        return int(lib.ec_pipeline_contention_events(self._h))
+
     def last_kernel(self):
         return lib.ec_pipeline_last_kernel(self._h).decode()
 
@@ -378,6 +382,11 @@ def _device_list(devices):
     if not devs:
         raise ValueError("empty device list")
     return (C.c_int * len(devs))(*devs), len(devs)
+
+
+def debug_hold_sms(device, stream, sms, microseconds):
+    """Test hook (ec_debug_hold_sms): occupy `sms` SMs of `device` for `microseconds` on `stream`."""
+    check(lib.ec_debug_hold_sms(int(device), _stream_arg(stream), int(sms), int(microseconds)))
 
 
 def plan_shard(count, ndev, idx):

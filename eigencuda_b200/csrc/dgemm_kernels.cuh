@@ -92,6 +92,21 @@ struct GemmParams {
   unsigned *sk_flags;      // gridDim.x flags; flag[c] == sk_epoch <=> CTA c's partial is published
   unsigned sk_epoch;       // unique per launch, so flags never need resetting
   int c_vec2;              // C base, ldc and batch stride are 16-byte aligned: row pairs may use 16 B stores
+  // Data-parallel tiles are handed out dynamically when dp_counter is set: the CTA's first tile is
+  // sk_tiles + blockIdx.x, every further one is sk_tiles + gridDim.x + (atomicAdd(dp_counter, 1) -
+  // dp_base).  The counter is never reset: the host knows how many claims a launch makes.
+  unsigned long long *dp_counter;
+  unsigned long long dp_base;
+  int dp_all_dynamic;      // 1: the first tile of a CTA is claimed too (the GPU is known to be shared:
+                           //    a CTA that has to wait for its SM must not sit on a tile meanwhile)
+  // Start-skew check of a persistent grid: stats[launch_parity] = earliest CTA start of this launch
+  // (globaltimer ns; the other slot is re-armed for the next launch).  A CTA that starts more than
+  // skew_limit_ns after the earliest one reports its lateness in *skew_out (host-mapped): it had
+  // to wait for an SM that some other kernel held.  Null = off.
+  unsigned long long *stats;
+  unsigned *skew_out;
+  unsigned skew_limit_ns;
+  int launch_parity;
   int pdl_trigger;         // where griddepcontrol.launch_dependents is issued: 0 never, 1 after the wait, 2 at kernel start, 3 before the first epilogue
   int sk_sms;              // SM count: CTAs b and b + sk_sms share an SM and get ADJACENT stream-K
                            // ranges, so their tile boundaries (epilogues) fall at different times
@@ -178,6 +193,19 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 }
 __device__ __forceinline__ void pdl_grid_dependency_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void st_shared_s64(uint32_t addr, long long v) {
+  asm volatile("st.shared.s64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_shared_s64(uint32_t addr) {
+  long long v;
+  asm volatile("ld.shared.s64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
 }
 // named barrier over the consumer warps only (barrier 0 is __syncthreads)
 __device__ __forceinline__ void consumer_bar_sync(int nthreads) {
@@ -270,10 +298,9 @@ struct Segment {
   int64_t tile;
   int kb0, kb1;
 };
+constexpr int TQ = 4;   // (power of two) depth of the tile queue between the producer and the consumers of a CTA
 struct Schedule {
   int64_t sk_it, sk_end;   // position / end inside the stream-K iteration space
-  int64_t dp_tile;         // next data-parallel tile
-  int64_t total_tiles;
   int kblocks;
   // Stream-K rank of this CTA.  The hardware places CTA b and b + #SMs on the same SM; giving
   // them consecutive ranks staggers their phases inside a tile by one CTA share.
@@ -284,32 +311,28 @@ struct Schedule {
   }
   __device__ __forceinline__ Schedule(const GemmParams &p, int kblocks_) {
     kblocks = kblocks_;
-    total_tiles = p.total_tiles;
     const int64_t S = p.sk_tiles * kblocks;
     const unsigned rank = sk_rank(p);
     sk_it = S * rank / gridDim.x;
     sk_end = S * (rank + 1) / gridDim.x;
-    dp_tile = p.sk_tiles + blockIdx.x;
   }
-  __device__ __forceinline__ bool next(Segment &sg) {
-    if (sk_it < sk_end) {
-      sg.tile = sk_it / kblocks;
-      sg.kb0 = (int)(sk_it - sg.tile * kblocks);
-      const int64_t left = sk_end - sk_it;
-      sg.kb1 = (int)(left < (int64_t)(kblocks - sg.kb0) ? sg.kb0 + left : kblocks);
-      sk_it += sg.kb1 - sg.kb0;
-      return true;
-    }
-    if (dp_tile < total_tiles) {
-      sg.tile = dp_tile;
-      sg.kb0 = 0;
-      sg.kb1 = kblocks;
-      dp_tile += gridDim.x;
-      return true;
-    }
-    return false;
+  // next segment of this CTA's share of the stream-K region (static: both sides compute it)
+  __device__ __forceinline__ bool next_sk(Segment &sg) {
+    if (sk_it >= sk_end) return false;
+    sg.tile = sk_it / kblocks;
+    sg.kb0 = (int)(sk_it - sg.tile * kblocks);
+    const int64_t left = sk_end - sk_it;
+    sg.kb1 = (int)(left < (int64_t)(kblocks - sg.kb0) ? sg.kb0 + left : kblocks);
+    sk_it += sg.kb1 - sg.kb0;
+    return true;
   }
 };
+// After the stream-K region come whole ("data-parallel") tiles.  Which ones is decided by the
+// producer thread alone -- statically (tile += gridDim.x) or by claiming them from a global counter
+// -- and passed to the consumer warps through a TQ-deep queue in shared memory (tile id + a
+// full/empty mbarrier pair per slot; -1 ends the stream).  With dynamic claims a CTA that starts
+// late or shares its SM with somebody else's kernel simply takes fewer tiles: the grid no longer
+// runs at the pace of its most delayed CTA.
 
 // ------------------------------------------------------------------------------------------
 // The hot kernel
@@ -324,9 +347,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled TMA destinations need 1024-byte alignment.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES]
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tile queue
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  static_assert(2 * STAGES * 8 <= 96, "barrier area layout");
+  auto tq_full = [&](int q) { return bar_base + 96u + 8u * q; };
+  auto tq_empty = [&](int q) { return bar_base + 96u + 8u * (TQ + q); };
+  auto tq_tile = [&](int q) { return bar_base + 96u + 8u * (2 * TQ + q); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -341,6 +368,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);                // one arrive.expect_tx by the producer
       mbar_init(empty_bar(s), CONSUMER_WARPS);  // one arrive per consumer warp
+    }
+#pragma unroll
+    for (int q = 0; q < TQ; ++q) {
+      mbar_init(tq_full(q), 1);                 // the producer, after writing the tile id
+      mbar_init(tq_empty(q), CONSUMER_WARPS);   // one arrive per consumer warp, after reading it
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -357,7 +389,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
   // underneath a running one (triggering before the wait lets a whole queue of launches pile
   // into the SMs' free slots).
   if (p.pdl_trigger == 1) pdl_launch_dependents();
-
   const int kblocks = (int)((p.K + BK - 1) / BK);
   const int tiles_per_problem = p.tiles_m * p.tiles_n;
 
@@ -365,11 +396,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
     // ===================== TMA producer (one elected lane) =====================
     if (Cfg::REGSPLIT) setmaxnreg_dec<Cfg::PRODUCER_REGS>();
     if (warp == CONSUMER_WARPS && lane == 0) {
+      // when did this CTA get its SM?  (compared with the rest of the grid once the loads are out)
+      const unsigned long long t_start = p.stats ? globaltimer_ns() : 0ull;
+      if (p.stats && blockIdx.x == 0) p.stats[p.launch_parity ^ 1] = ~0ull;   // re-arm the next launch's slot
       int stage = 0;
       uint32_t phase = 0;
-      Schedule sched(p, kblocks);
-      Segment sg;
-      while (sched.next(sg)) {
+      auto load_segment = [&](const Segment &sg) {
         const int b = (int)(sg.tile / tiles_per_problem);
         const int r = (int)(sg.tile - (int64_t)b * tiles_per_problem);
         const int m0 = (r % p.tiles_m) * BM;
@@ -386,6 +418,57 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
             stage = 0;
             phase ^= 1u;
           }
+        }
+      };
+      Schedule sched(p, kblocks);
+      Segment sg;
+      while (sched.next_sk(sg)) load_segment(sg);
+      // whole tiles: the first one is fixed, further ones are claimed one tile ahead of their use
+      // (the round trip of the atomic hides behind the loads of the tile in between)
+      const int64_t dyn_first = p.sk_tiles + (p.dp_all_dynamic ? 0 : (int64_t)gridDim.x);
+      auto claim = [&]() -> int64_t {
+        return dyn_first + (int64_t)(atomicAdd(p.dp_counter, 1ull) - p.dp_base);
+      };
+      // A CTA's first whole tile is fixed unless every tile is claimed (dp_all_dynamic): both sides
+      // know it without talking.  The queue carries what comes after it -- and nothing at all when
+      // no CTA can have a second tile (single-wave grids: the latency-bound small products).
+      const bool first_static = !p.dp_all_dynamic;
+      const bool queued = p.dp_all_dynamic || p.total_tiles - p.sk_tiles > (int64_t)gridDim.x;
+      int64_t cur = first_static ? p.sk_tiles + blockIdx.x : claim();
+      int64_t nxt = p.total_tiles;   // invalid
+      if (cur < p.total_tiles && queued) nxt = p.dp_counter ? claim() : cur + gridDim.x;
+      int q = 0;
+      uint32_t qphase = 0;
+      for (bool first = first_static;; first = false) {
+        const bool valid = cur < p.total_tiles;
+        if (queued && !(first && valid)) {   // the fixed first tile is not queued
+          mbar_wait(tq_empty(q), qphase ^ 1u);
+          st_shared_s64(tq_tile(q), valid ? (long long)cur : -1ll);
+          mbar_arrive(tq_full(q));
+          if (++q == TQ) {
+            q = 0;
+            qphase ^= 1u;
+          }
+        }
+        if (!valid) break;
+        int64_t nn = p.total_tiles;
+        if (nxt < p.total_tiles) nn = p.dp_counter ? claim() : nxt + gridDim.x;
+        sg.tile = cur;
+        sg.kb0 = 0;
+        sg.kb1 = kblocks;
+        load_segment(sg);
+        if (!queued) break;
+        cur = nxt;
+        nxt = nn;
+      }
+      // Start-skew check, here where it delays nobody: this thread has nothing left to do.  A CTA
+      // that started much later than the first one of the grid had to wait for an SM that some
+      // other kernel held; it says so in host-mapped memory, where the dispatcher finds it.
+      if (p.stats) {
+        const unsigned long long first = atomicMin(p.stats + p.launch_parity, t_start);
+        if (first < t_start && t_start - first > p.skew_limit_ns) {
+          const unsigned long long late = t_start - first;
+          atomicMax(p.skew_out, late > 0xffffffffull ? 0xffffffffu : (unsigned)late);
         }
       }
     }
@@ -405,14 +488,71 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
   uint32_t pending_bar = 0;  // empty barrier of the slot consumed last, not yet released
   Schedule sched(p, kblocks);
   Segment sg;
-  while (sched.next(sg)) {
+  // whole tiles: state of the consumer side of the tile queue.  qn >= 0: pops so far modulo 2*TQ
+  // (slot = qn % TQ, parity = (qn / TQ) & 1); -1: the stream has ended; -2: the CTA's fixed first
+  // tile is still to be done (it is not queued, see the producer)
+  const bool queued = p.dp_all_dynamic || p.total_tiles - p.sk_tiles > (int64_t)gridDim.x;
+  int qn = p.dp_all_dynamic ? 0 : -2;
+  // A stream-K tile this CTA owns (it computed the tile's first k-iterations) is finished LAST,
+  // after the CTA's whole data-parallel share: its accumulators wait in the workspace meanwhile.
+  // By then the other contributors' partials have long been published, so the owner hardly ever
+  // spins -- and no CTA spins in the middle of its work, which is what lets the grid be launched
+  // without a co-residency guarantee (a CTA that cannot become resident yet only delays the
+  // finishing touches of the tiles it contributes to, not the data-parallel work of the others).
+  int own_tile = -1, own_kb1 = 0;   // (stream-K tiles come first in the numbering: they fit an int)
+  // spill slot of the owner: behind the gridDim.x contributor slots
+  auto own_ws = [&]() -> double * {
+    return p.sk_workspace + ((size_t)gridDim.x + Schedule::sk_rank(p)) * (BM * BN) + threadIdx.x;
+  };
+  for (;;) {
+    bool resume = false;
+    if (sched.next_sk(sg)) {
+    } else if (qn == -2) {
+      qn = queued ? 0 : -1;
+      if (p.sk_tiles + blockIdx.x >= p.total_tiles) continue;   // no first tile: nothing follows either
+      sg.tile = p.sk_tiles + blockIdx.x;
+      sg.kb0 = 0;
+      sg.kb1 = kblocks;
+    } else if (qn >= 0) {
+      const int q = qn & (TQ - 1);
+      mbar_wait(tq_full(q), (uint32_t)(qn / TQ) & 1u);
+      const long long t = ld_shared_s64(tq_tile(q));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tq_empty(q));
+      if (t < 0) {
+        qn = -1;
+        continue;
+      }
+      qn = (qn + 1) & (2 * TQ - 1);
+      sg.tile = t;
+      sg.kb0 = 0;
+      sg.kb1 = kblocks;
+    } else if (own_tile >= 0) {
+      sg.tile = own_tile;
+      sg.kb0 = 0;
+      sg.kb1 = own_kb1;
+      own_tile = -1;
+      resume = true;
+    } else {
+      break;
+    }
     double acc[MB][NB][2];
+    if (resume) {
+      const double *ws = own_ws();
 #pragma unroll
-    for (int i = 0; i < MB; ++i)
+      for (int i = 0; i < MB; ++i)
 #pragma unroll
-      for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NB; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) acc[i][j][e] = __ldcg(ws + ((i * NB + j) * 2 + e) * CONSUMER_THREADS);
+    } else {
+#pragma unroll
+      for (int i = 0; i < MB; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    }
 
-    for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+    for (int kb = resume ? sg.kb1 : sg.kb0; kb < sg.kb1; ++kb) {
       mbar_wait(full_bar(stage), phase);
       // Deferred slot release: the slot of the PREVIOUS k-iteration is handed back only now.
       // An arrive issued right behind the loads of its own stage carries no scoreboard wait,
@@ -451,9 +591,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
 
     // ---- stream-K fix-up -------------------------------------------------------------------
     // A segment that does not start the tile publishes its partial sums (it is always the first
-    // thing this CTA computes).  The segment that starts a tile but does not finish it (always
-    // the last thing this CTA computes in the region) owns the tile: it adds, in CTA order, the
-    // partials of the CTAs that follow it -- published long before -- and writes C.
+    // thing this CTA computes).  The segment that starts a tile but does not finish it owns the
+    // tile: it parks its accumulators, and after the CTA's data-parallel tiles it adds, in CTA
+    // order, the partials of the CTAs that follow it -- published long before -- and writes C.
     //
     // Deep splits (a 64 x 64 product over K = 10^6 is cut over every CTA of the grid) would make
     // that a serial chain of hundreds of dependent workspace reads in ONE CTA.  Beyond
@@ -500,6 +640,20 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
         __threadfence();
         consumer_bar_sync(CONSUMER_THREADS);
         if (threadIdx.x == 0) st_release_gpu(p.sk_flags + rank, p.sk_epoch);
+        continue;
+      }
+      if (!resume && p.total_tiles > p.sk_tiles) {
+        // owner, first visit, and there are data-parallel tiles to do: park the accumulators
+        // and come back after them
+        double *ws = own_ws();
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) __stcg(ws + ((i * NB + j) * 2 + e) * CONSUMER_THREADS, acc[i][j][e]);
+        own_tile = (int)sg.tile;
+        own_kb1 = sg.kb1;
         continue;
       }
       if (tree) {
@@ -592,6 +746,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
       }
     }
   }
+
 }
 
 // ------------------------------------------------------------------------------------------
@@ -674,6 +829,16 @@ __global__ void __launch_bounds__(SIMT_THREADS) dgemm_simt_kernel(const SimtPara
         C[col * p.ldc + row] = v;
       }
     }
+  }
+}
+
+// Test hook: a kernel that does nothing but hold SMs -- `gridDim.x` CTAs, each filling its SM's
+// shared memory so that nothing else fits beside it, spinning for `ns` nanoseconds.
+__global__ void hold_sms_kernel(unsigned long long ns) {
+  extern __shared__ uint8_t hold_smem[];
+  if (threadIdx.x == 0) hold_smem[0] = 1;
+  const unsigned long long t0 = globaltimer_ns();
+  while (globaltimer_ns() - t0 < ns) {
   }
 }
 

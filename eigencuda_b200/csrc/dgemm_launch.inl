@@ -60,14 +60,32 @@ int make_tensor_map(ec_pipeline *p, CUtensorMap *tm, const Operand &o, int64_t b
   return EC_OK;
 }
 
-constexpr size_t SK_WORKSPACE_BYTES = (size_t)640 * 128 * 128 * 8 / 4;  // >= grid * BM*BN*8 for every config
+// >= 2 * grid * BM*BN*8 for every config: one contributor slot and one owner spill slot per CTA
+constexpr size_t SK_WORKSPACE_BYTES = (size_t)2 * 640 * 128 * 128 * 8 / 4;
 constexpr int SK_MAX_GRID = 1024;
+constexpr unsigned CONTENDED_SKEW_NS = 50000;   // CTAs of one persistent grid starting > 50 us apart: somebody else holds SMs
+constexpr int CONTENDED_LAUNCHES = 32;          // launches that avoid static partitions after that, before probing again
 
 int ensure_sk_workspace(ec_pipeline *p) {
   if (p->sk_workspace) return EC_OK;
   EC_CUDA(cudaMalloc((void **)&p->sk_workspace, SK_WORKSPACE_BYTES));
   EC_CUDA(cudaMalloc((void **)&p->sk_flags, SK_MAX_GRID * sizeof(unsigned)));
   EC_CUDA(cudaMemsetAsync(p->sk_flags, 0, SK_MAX_GRID * sizeof(unsigned), p->stream));
+  return EC_OK;
+}
+
+// Scheduler words of a pipeline: the claim counter of the dynamic tile schedule, the start-skew
+// statistics of persistent grids (device memory) and the word the kernel reports the skew in
+// (host memory mapped into the device, read by the dispatcher without any synchronisation).
+int ensure_sched_words(ec_pipeline *p) {
+  if (p->sched_words) return EC_OK;
+  EC_CUDA(cudaMalloc((void **)&p->sched_words, 4 * sizeof(unsigned long long)));
+  const unsigned long long init[4] = {0ull, ~0ull, ~0ull, 0ull};   // claim counter, earliest CTA start (two slots, by launch parity)
+  EC_CUDA(cudaMemcpyAsync(p->sched_words, init, sizeof(init), cudaMemcpyHostToDevice, p->stream));
+  EC_CUDA(cudaStreamSynchronize(p->stream));   // `init` is on this stack frame
+  EC_CUDA(cudaHostAlloc((void **)&p->skew_host, sizeof(unsigned), cudaHostAllocMapped));
+  *p->skew_host = 0;
+  EC_CUDA(cudaHostGetDevicePointer((void **)&p->skew_dev, (void *)p->skew_host, 0));
   return EC_OK;
 }
 
@@ -105,11 +123,23 @@ int launch_tma_dmma(ec_pipeline *p, const CUtensorMap &tmA, const CUtensorMap &t
   gp.sk_flags = nullptr;
   gp.sk_epoch = 0;
   gp.pdl_trigger = p->pdl;
+  // Is the GPU being shared?  The last persistent grid reported how far apart its CTAs started:
+  // microseconds on an idle GPU, as long as the other kernel runs when some of them had to wait
+  // for SMs it held.  A statically cut stream-K region then runs at the pace of the CTA that
+  // started last, so for the next launches the region is dropped and the work is handed out
+  // dynamically (long tiles: one CTA per tile, balanced by the hardware).  Re-probed afterwards.
+  if (p->skew_host && *(volatile unsigned *)p->skew_host > CONTENDED_SKEW_NS) {
+    p->contended_left = CONTENDED_LAUNCHES;
+    p->contended_events++;
+    *(volatile unsigned *)p->skew_host = 0;
+  }
+  const bool contended = p->contended_left > 0;
+  if (contended) p->contended_left--;
   // Stream-K region: the tiles of the last, partial wave plus (when there is one) one full wave,
   // so that every CTA gets between one and two tiles' worth of k-iterations in the region.
   const int64_t rem = gp.total_tiles % slots;
-  if (want_sk && p->stream_k && (rem != 0 || getenv("EC_SK_ALL")) && slots <= SK_MAX_GRID &&
-      slots * (int64_t)(Cfg::BM * Cfg::BN * 8) <= (int64_t)SK_WORKSPACE_BYTES) {
+  if (want_sk && !contended && p->stream_k && (rem != 0 || getenv("EC_SK_ALL")) && slots <= SK_MAX_GRID &&
+      2 * slots * (int64_t)(Cfg::BM * Cfg::BN * 8) <= (int64_t)SK_WORKSPACE_BYTES) {
     int64_t sk_tiles = rem + (gp.total_tiles > slots ? slots : 0);
     if (const char *e = getenv("EC_SK_ALL")) {   // experiment: stream-K over every tile
       if (atoi(e)) sk_tiles = gp.total_tiles;
@@ -125,16 +155,45 @@ int launch_tma_dmma(ec_pipeline *p, const CUtensorMap &tmA, const CUtensorMap &t
       grid = (int)slots;
     }
   }
-  if (gp.sk_tiles == 0 && p->one_cta_per_tile && kblocks >= 64 && gp.total_tiles > slots)
+  if (gp.sk_tiles == 0 && (p->one_cta_per_tile || contended) && kblocks >= 64 && gp.total_tiles > slots)
     grid = (int)std::min<int64_t>(gp.total_tiles, (int64_t)1 << 30);   // one tile per CTA
-  if (gp.sk_tiles > 0) {
-    // CTAs wait on one another's partials: a cooperative launch guarantees co-residency.
-    void *args[3] = {(void *)&tmA, (void *)&tmB, (void *)&gp};
-    EC_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(Cfg::THREADS), args,
-                                        (size_t)Cfg::SMEM_BYTES, p->stream));
-  } else {
-    // programmatic dependent launch: this grid may become resident while its predecessor in the
-    // stream is still running; the kernel waits (griddepcontrol.wait) before it touches memory
+  // Whole tiles beyond each CTA's first are claimed dynamically when tiles are long enough for
+  // the claim's round trip to hide behind the loads of the tile before (8 k-iterations).
+  const int64_t dp_tiles = gp.total_tiles - gp.sk_tiles;
+  gp.dp_counter = nullptr;
+  gp.dp_base = 0;
+  gp.dp_all_dynamic = 0;
+  gp.stats = nullptr;
+  gp.skew_out = nullptr;
+  gp.skew_limit_ns = 0;
+  gp.launch_parity = 0;
+  const bool persistent = (int64_t)grid <= slots;
+  if (persistent && p->dynamic_tiles) {
+    rc = ensure_sched_words(p);
+    if (rc) return rc;
+    if (contended && dp_tiles > 0) {   // every tile claimed, the first one of each CTA included
+      gp.dp_counter = p->sched_words;
+      gp.dp_base = p->dp_claims;
+      gp.dp_all_dynamic = 1;
+      p->dp_claims += (unsigned long long)dp_tiles + (unsigned long long)grid;   // successes + one miss per CTA
+    } else if (dp_tiles > grid && kblocks >= 8) {
+      gp.dp_counter = p->sched_words;
+      gp.dp_base = p->dp_claims;
+      p->dp_claims += (unsigned long long)dp_tiles;   // (dp_tiles - grid) successes + one miss per CTA
+    }
+    if (grid >= p->sm_count / 2) {   // a grid wide enough for its start skew to say something about the GPU
+      gp.stats = p->sched_words + 1;
+      gp.skew_out = p->skew_dev;
+      gp.skew_limit_ns = CONTENDED_SKEW_NS;
+      gp.launch_parity = (int)(p->stats_launches++ & 1);
+    }
+  }
+  {
+    // Programmatic dependent launch: this grid may become resident while its predecessor in the
+    // stream is still running; the kernel waits (griddepcontrol.wait) before it touches memory.
+    // No cooperative launch any more, stream-K included: contributors never wait, owners wait only
+    // at the very end of their work, and the grid never exceeds what the device can hold at once,
+    // so every CTA gets an SM as soon as other kernels release theirs.
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(Cfg::THREADS);

@@ -74,6 +74,7 @@ static int pipeline_create_impl(int device, cudaStream_t external, bool use_exte
                 prop.major, prop.minor);
   ec_pipeline *p = new ec_pipeline();
   p->device = dev;
+  if (const char *e = std::getenv("EC_DYNAMIC_TILES")) p->dynamic_tiles = std::atoi(e) != 0;
   if (const char *e = std::getenv("EC_PDL")) p->pdl = std::max(0, std::min(3, std::atoi(e)));
   p->sm_count = prop.multiProcessorCount;
   if (use_external) {
@@ -147,6 +148,8 @@ int ec_pipeline_destroy(ec_pipeline *p) {
   delete p->compat_pool;
   p->compat_pool = nullptr;
   if (p->ev_order) cudaEventDestroy(p->ev_order);
+  if (p->sched_words) cudaFree(p->sched_words);
+  if (p->skew_host) cudaFreeHost(p->skew_host);
   if (p->sk_workspace) cudaFree(p->sk_workspace);
   if (p->sk_flags) cudaFree(p->sk_flags);
   if (p->oz_planes_a) cudaFree(p->oz_planes_a);
@@ -206,6 +209,7 @@ int ec_plan_dgemm(int sm_count, int64_t m, int64_t n, int64_t k, int64_t batch, 
   return EC_OK;
 }
 int64_t ec_pipeline_launch_count(const ec_pipeline *p) { return p ? p->launches : 0; }
+int64_t ec_pipeline_contention_events(const ec_pipeline *p) { return p ? p->contended_events : 0; }
 const char *ec_pipeline_last_kernel(const ec_pipeline *p) { return p ? p->last_kernel : "none"; }
 
 int ec_pipeline_set_stream_config(ec_pipeline *p, int chunk_matrices, int ring_depth,
@@ -730,6 +734,16 @@ int ec_fill_uniform_block(ec_pipeline *p, uint64_t seed, uint64_t matrix_id, dou
   p->launches++;
   return EC_OK;
 }
+int ec_debug_hold_sms(int device, void *cuda_stream, int sms, int64_t microseconds) {
+  if (sms <= 0 || microseconds < 0) return fail(EC_ERR_ARG, "bad hold request");
+  DeviceGuard guard(device);
+  constexpr int SMEM = 200 * 1024;
+  EC_CUDA(cudaFuncSetAttribute(ec::hold_sms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  ec::hold_sms_kernel<<<sms, 32, SMEM, (cudaStream_t)cuda_stream>>>((unsigned long long)microseconds * 1000ull);
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
 int ec_fill_uniform(ec_pipeline *p, uint64_t seed, uint64_t matrix_id, double *dst, int64_t count) {
   return ec_fill_uniform_batched(p, seed, matrix_id, dst, count, 1);
 }

@@ -33,6 +33,14 @@ struct ec_pipeline {
   int stream_k = 1;   // 0 disables the stream-K schedule (EC_STREAM_K=0)
   int sm_margin = 0;  // SMs left free for concurrent kernels (NCCL during SUMMA)
   int one_cta_per_tile = 0;  // non-persistent launch for long tiles (shared-GPU friendly)
+  // dynamic tile schedule + contention detection (dgemm_launch.inl: ensure_sched_words)
+  int dynamic_tiles = 1;                       // EC_DYNAMIC_TILES=0: static round-robin, no statistics
+  unsigned long long *sched_words = nullptr;   // device: [0] claim counter, [1..3] start-skew statistics
+  unsigned long long dp_claims = 0;            // claims made so far (the counter is never reset)
+  unsigned *skew_host = nullptr, *skew_dev = nullptr;   // host-mapped: start skew (ns) of the last persistent grid
+  unsigned long long stats_launches = 0;       // launches that carried the start-skew check (slot parity)
+  int contended_left = 0;                      // launches left in "the GPU is shared" mode
+  int64_t contended_events = 0;                // how often that mode was entered
   int pdl = 1;               // programmatic dependent launch of the GEMM kernels (EC_PDL=0 turns it off)
   // small direct-mapped cache of encoded tensor maps: the compat loop and every tensor-stream
   // chunk reuse the same few device buffers, and cuTensorMapEncodeTiled costs about a microsecond

@@ -266,6 +266,14 @@ int ec_fill_uniform_batched(ec_pipeline *p, uint64_t seed, uint64_t first_id, do
 int ec_fill_uniform_block(ec_pipeline *p, uint64_t seed, uint64_t matrix_id, double *dst,
                           int64_t rows, int64_t cols, int64_t ld_dst, int64_t row0, int64_t col0,
                           int64_t global_ld);
+/* How often the dispatcher of this pipeline has found the GPU shared with somebody else's kernels
+ * (CTAs of one of its persistent grids started more than 50 us apart) and switched, for the next
+ * 32 launches, from statically partitioned schedules (stream-K, round-robin tiles) to dynamic ones
+ * (tiles claimed from a counter; long tiles one CTA each).  See DESIGN.md section 3.1. */
+int64_t ec_pipeline_contention_events(const ec_pipeline *p);
+/* Test hook: occupy `sms` streaming multiprocessors of `device` for `microseconds` with a kernel
+ * that does nothing (one CTA per SM, sized so that no other CTA fits beside it), on `cuda_stream`. */
+int ec_debug_hold_sms(int device, void *cuda_stream, int sms, int64_t microseconds);
 /* Launch counter: number of kernels this library has launched on this pipeline since creation. */
 int64_t ec_pipeline_launch_count(const ec_pipeline *p);
 /* Name of the kernel variant the last ec_dgemm* on this pipeline dispatched to. */

@@ -309,6 +309,77 @@ def test_stream_k_batched(pipe, monkeypatch):
         assert orc.rel_frobenius(got[:, :, i], orc.cpu_product(orc.fill_uniform(orc.SEED, i + 1, (n, n)), F)) <= TOL
 
 
+def test_dynamic_tile_schedule_matches_static(monkeypatch):
+    """Whole tiles claimed from a counter (the default for tiles of 8+ k-iterations) give the same
+    bits as the static round-robin schedule: which CTA computes a tile does not change its sums."""
+    shapes = [(2048, 2048, 512, 1), (1000, 1000, 1000, 7), (512, 512, 512, 64), (640, 384, 2048, 3)]
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("EC_DYNAMIC_TILES", mode)
+        monkeypatch.setenv("EC_STREAM_K", "0")
+        p = ec.CudaPipeline(0)
+        for (m, n, k, batch) in shapes:
+            A, B = rnd(31, (m * batch, k)), rnd(32, (k, n))
+            dA, dB = ec.CudaMatrix(A, p.get_stream()), ec.CudaMatrix(B, p.get_stream())
+            dC = ec.CudaMatrix(m * batch, n, p.get_stream())
+            for _ in range(3):          # repeated launches: the claim counter is never reset
+                p.dgemm(0, 0, m * batch, n, k, 1.0, dA.data(), m * batch, dB.data(), k, 0.0, dC.data(), m * batch)
+            got = dC.to_eigen()
+            outs.setdefault((m, n, k, batch), []).append(got)
+            assert orc.rel_frobenius(got, orc.dgemm(A, B, flavour="fast")) <= TOL
+        p.close()
+    for key, (a, b) in outs.items():
+        assert np.array_equal(a, b), key
+
+
+def test_shared_gpu_is_detected_and_schedules_adapt(monkeypatch):
+    """a statically partitioned grid (stream-K above all) runs at the pace of the CTA
+    that gets its SM last.  With another kernel holding 24 of the 148 SMs, a static grid takes two
+    rounds (the CTAs that found no SM start when the first ones leave: 2.0x); with tiles claimed
+    dynamically the first product already does better, it reports the start skew of its CTAs, and
+    from the next launch on the dispatcher drops the stream-K region too (1.3x, the ideal being
+    148/124 = 1.19x).  Launches are plain (no cooperative launch), results unchanged."""
+    import time
+    import torch
+    n = 4096
+    side = torch.cuda.Stream()
+    A, B = rnd(41, (n, n)), rnd(42, (n, n))
+
+    def measure(dynamic):
+        monkeypatch.setenv("EC_DYNAMIC_TILES", "1" if dynamic else "0")
+        p = ec.CudaPipeline(0)
+        dA, dB = ec.CudaMatrix(A, p.get_stream()), ec.CudaMatrix(B, p.get_stream())
+        dC = ec.CudaMatrix(n, n, p.get_stream())
+        run = lambda: p.dgemm(0, 0, n, n, n, 1.0, dA.data(), n, dB.data(), n, 0.0, dC.data(), n)
+        for _ in range(2):
+            run()
+        p.synchronize()
+        assert p.last_kernel().endswith("_sk") and p.contention_events() == 0
+        quiet = dC.to_eigen()
+        times, kernels = [], []
+        for _ in range(3):
+            ec.debug_hold_sms(0, side.cuda_stream, 24, 40000)     # 24 SMs taken for 40 ms
+            time.sleep(0.003)                                     # let it become resident
+            t0 = time.perf_counter()
+            run()
+            p.synchronize()
+            times.append((time.perf_counter() - t0) * 1e3)
+            kernels.append(p.last_kernel())
+            side.synchronize()
+            assert np.array_equal(dC.to_eigen(), quiet) or orc.rel_frobenius(dC.to_eigen(), quiet) <= 1e-14
+        events = p.contention_events()
+        p.close()
+        return times, kernels, events, quiet
+
+    t_static, k_static, e_static, ref = measure(False)
+    t_dyn, k_dyn, e_dyn, got = measure(True)
+    assert e_static == 0 and all(k.endswith("_sk") for k in k_static)
+    assert e_dyn >= 1 and k_dyn[0].endswith("_sk") and not k_dyn[-1].endswith("_sk"), (k_dyn, e_dyn)
+    assert t_dyn[-1] < 0.85 * t_static[-1], (t_static, t_dyn)       # measured 4.95 ms against 7.57 ms
+    assert orc.rel_frobenius(got[:64], orc.dgemm(A[:64], B, flavour="fast")) <= TOL
+    assert orc.rel_frobenius(got, ref) <= 1e-14
+
+
 def test_one_cta_per_tile_schedule(pipe):
     """The non-persistent launch (one CTA per tile, for long-K tiles on a shared GPU) computes the
     same bits as the persistent grid."""
