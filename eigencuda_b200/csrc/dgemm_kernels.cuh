@@ -70,6 +70,9 @@ using CfgL  = TileCfg<128, 128, 64, 32, 5, 1, true>;    // 8 consumer warps, 160
 using CfgS  = TileCfg< 64,  64, 32, 32, 4, 2, false>;   // 4 consumer warps,  64 KiB, 2 CTAs/SM
 using CfgXS = TileCfg< 64,  32, 32, 16, 4, 3, false>;   // 4 consumer warps,  48 KiB, 3 CTAs/SM
 using CfgT  = TileCfg< 32,  32, 16, 16, 4, 5, false>;   // 4 consumer warps,  33 KiB, 5 CTAs/SM (80 regs; 6 would spill): tensors of matrices of 32 x 32 and less
+// (An 8-deep ring for the 32x32 tile was measured in round 2 for the small single-wave products -- n = 128..384
+//  unchanged, 7.1 vs 7.2 us back to back, n >= 512 slower for the lost occupancy: they are bound by launch and
+//  prologue, not by the TMA round trip -- and is not built.)
 using CfgN  = TileCfg<128,  16, 32, 16, 4, 3, false>;   // 4 consumer warps,  73 KiB, 3 CTAs/SM: skinny products with at most 16 columns --
                                                         // a 32-wide tile would spend half its DMMAs on padding, which is what bounds these HBM-bound shapes
 // (A 128x64 / 2 CTAs-per-SM variant and register-split variants of the small tiles were measured
@@ -350,10 +353,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tile queue
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  static_assert(2 * STAGES * 8 <= 96, "barrier area layout");
-  auto tq_full = [&](int q) { return bar_base + 96u + 8u * q; };
-  auto tq_empty = [&](int q) { return bar_base + 96u + 8u * (TQ + q); };
-  auto tq_tile = [&](int q) { return bar_base + 96u + 8u * (2 * TQ + q); };
+  static_assert(2 * STAGES * 8 <= 128, "barrier area layout");
+  auto tq_full = [&](int q) { return bar_base + 128u + 8u * q; };
+  auto tq_empty = [&](int q) { return bar_base + 128u + 8u * (TQ + q); };
+  auto tq_tile = [&](int q) { return bar_base + 128u + 8u * (2 * TQ + q); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

@@ -6,7 +6,7 @@ import eigencuda_b200 as ec
 dev = torch.device("cuda", 0); stream = torch.cuda.current_stream()
 pipe = ec.CudaPipeline(0, stream=stream.cuda_stream)
 out = []
-for (n, tile, sk) in ((1024, 2, 0), (1024, 2, 2), (512, 4, 0), (640, 4, 0), (2048, 1, 2), (2048, 1, 0), (4096, 1, 0)):
+for (n, tile, sk) in [tuple(int(v) for v in x.split(':')) for x in os.environ.get('AB_CASES', '1024:2:0,1024:2:2,512:4:0,640:4:0,2048:1:2,2048:1:0,4096:1:0').split(',')]:
     os.environ["EC_FORCE_TILE"] = str(tile); os.environ["EC_STREAM_K"] = str(sk)
     A = torch.randn((n, n), dtype=torch.float64, device=dev); B = torch.randn((n, n), dtype=torch.float64, device=dev)
     C = torch.empty((n, n), dtype=torch.float64, device=dev)
@@ -20,5 +20,10 @@ for (n, tile, sk) in ((1024, 2, 0), (1024, 2, 2), (512, 4, 0), (640, 4, 0), (204
         for _ in range(50): fn()
         b.record(stream); b.synchronize()
         best = min(best, a.elapsed_time(b) / 50 * 1e3)
-    out.append(f"n={n} tile={tile} sk={sk}: {best:7.1f} ({pipe.last_kernel()})")
+    one = 1e9
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream); fn(); b.record(stream); b.synchronize()
+        one = min(one, a.elapsed_time(b) * 1e3)
+    out.append(f"n={n} tile={tile} sk={sk}: {best:7.1f}/{one:6.1f} ({pipe.last_kernel()})")
 print(f"lib={'old' if os.environ.get('EIGENCUDA_B200_LIB') else 'new'} DYN={os.environ.get('EC_DYNAMIC_TILES','1')} PDL={os.environ.get('EC_PDL','1')} | " + " | ".join(out), flush=True)

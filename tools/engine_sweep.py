@@ -53,7 +53,7 @@ for ring in [int(x) for x in args.rings.split(",")]:
             call()
             dt = time.perf_counter() - t0
             best, tot = min(best, dt), tot + dt
-        print(json.dumps({"chunk": chunk, "ring": ring, "chunk_mib": chunk * elems * 8 / 2**20,
+        print(json.dumps({"chunk": chunk or "default (64 MiB, ramped)", "ring": ring, "chunk_mib": chunk * elems * 8 / 2**20,
                           "matrices_per_s_avg": total * reps / tot, "matrices_per_s_best": total / best,
                           "gbs_each_way_avg": total * elems * 8 * reps / tot / 1e9}), flush=True)
 print(json.dumps({"link_after": ec.host_link_probe(devices, 256 << 20, 5)}), flush=True)
