@@ -50,7 +50,7 @@ int tensor_stream_run_impl(ec_pipeline *p, int kind, const double *F, int64_t f_
   if (chunk <= 0) chunk = std::max<int64_t>(1, ((int64_t)64 << 20) / (8 * std::max(t_sz, r_sz)));
   chunk = std::min(chunk, count);
   const std::vector<int64_t> starts = plan_chunks(count, chunk, ramp);
-  const int ring = p->cfg_ring > 0 ? p->cfg_ring : 3;
+  const int ring = p->cfg_ring > 0 ? p->cfg_ring : 4;
   int threads = p->cfg_threads;
   if (threads <= 0) threads = std::max(2u, std::min(16u, std::thread::hardware_concurrency()));
   if (!p->engine) {
