@@ -633,6 +633,7 @@ def main():
         except Exception:
             hbm_peak = 6458.4   # B200_PROFILING.md fallback
         skinny = []
+        l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # 2x the 126 MB L2
         for (sm_, sn_, sk_) in ((1 << 20, 32, 32), (1 << 20, 16, 128), (1 << 20, 128, 16), (8192, 8192, 64)):
             A = torch.empty(sm_ * sk_, dtype=torch.float64, device=dev)
             B = torch.empty(sk_ * sn_, dtype=torch.float64, device=dev)
@@ -641,6 +642,7 @@ def main():
             pipe.fill_uniform(SEED, 1, B.data_ptr(), sk_ * sn_, 1)
             best = float("inf")
             for it in range(8):
+                l2_flush.zero_()                     # nothing of the operands left in L2 from the run before
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream)
                 pipe.dgemm(0, 0, sm_, sn_, sk_, 1.0, A.data_ptr(), sm_, B.data_ptr(), sk_, 0.0, Cm.data_ptr(), sm_)
@@ -654,7 +656,9 @@ def main():
                            "tflops": 2.0 * sm_ * sn_ * sk_ / best / 1e9, "kernel": pipe.last_kernel()})
             del A, B, Cm
         extras["skinny_hbm_bound"] = {"hbm_peak_gbs": hbm_peak, "shapes": skinny,
-                                      "note": "each shape moves 0.5-1.2 GB per call, far more than the 126 MB L2 holds"}
+                                      "note": "each shape moves 0.5-1.2 GB per call, far more than the 126 MB L2 holds; "
+                                              "L2 flushed (256 MiB written) before every timed call"}
+        del l2_flush
         torch.cuda.empty_cache()
         # configs[3]: 2000 x (1000x1000): A^T * B_i and A^T * M_i * A, resident in HBM
         n4, c4 = 1000, 2000
