@@ -308,6 +308,9 @@ def e2e_legs(args, ec, orc, pipe, torch, dev, world, Fh):
 
     def pinned_leg(devs):
         link = ec.host_link_probe(devs, 256 << 20, 5)
+        # ... and the same plain copies over the job's own 2 x 16 GiB buffers: as much unique host
+        # memory as the job touches, so the host's last-level cache cannot flatter the ceiling
+        link_job = ec.host_link_probe_buffers(devs, pin_in.ptr, pin_out.ptr, (total // len(devs)) * mbytes, 64 << 20, 2)
         pin_out.array[:, :] = 0.0
         for _ in range(2):
             call(in_ptrs, out_ptrs, total, devs)   # warm-up: engine rings, child pipelines, NCCL communicators
@@ -331,11 +334,17 @@ def e2e_legs(args, ec, orc, pipe, torch, dev, world, Fh):
                         f"call, one process, one worker thread + ring per GPU, NCCL broadcast of F inside the timed region"),
                 "tflops": rate * 2.0 * n ** 3 / 1e12, "gpu_launches_per_step": launches / esteps,
                 "link_gbs_each_way": gbs, "link_gbs_each_way_per_gpu": gbs / g,
-                "link_roofline_gbs": {"h2d_only": link["h2d"], "d2h_only": link["d2h"],
-                                      "bidirectional_each_way": link["bidir_each_way"],
-                                      "how": f"plain pinned cudaMemcpyAsync, 256 MiB per copy, on these {g} GPU(s) at once, best "
-                                             f"of 5, measured in this run just before the leg; GB/s summed over the GPUs"},
-                "frac_of_link": gbs / link["bidir_each_way"] if link["bidir_each_way"] else None}
+                "link_roofline_gbs": {"h2d_only": link_job["h2d"], "d2h_only": link_job["d2h"],
+                                      "bidirectional_each_way": link_job["bidir_each_way"],
+                                      "how": f"plain pinned cudaMemcpyAsync over the job's own buffers ({total * mbytes / 2**30:.0f} GiB each "
+                                             f"way, 64 MiB per copy, each of these {g} GPU(s) its own slice, all at once, best of 2), "
+                                             f"measured in this run just before the leg; GB/s summed over the GPUs",
+                                      "small_buffers": {"h2d_only": link["h2d"], "d2h_only": link["d2h"],
+                                                        "bidirectional_each_way": link["bidir_each_way"],
+                                                        "how": "the same with 256 MiB rotating buffers per GPU, best of 5 "
+                                                               "(can sit in the host's last-level cache)"}},
+                "frac_of_link": gbs / link_job["bidir_each_way"] if link_job["bidir_each_way"] else None,
+                "frac_of_link_small_buffers": gbs / link["bidir_each_way"] if link["bidir_each_way"] else None}
 
     e2e_all = pinned_leg(devices)
     if list(picked) != list(devices):

@@ -72,6 +72,7 @@ SIGNATURES = {
     "ec_pick_stream_devices": (_int, [C.POINTER(_int), _int, C.POINTER(_int), C.POINTER(_int), C.POINTER(_dbl)]),
     "ec_plan_shard": (_int, [_i64, _int, _int, C.POINTER(_i64), C.POINTER(_i64)]),
     "ec_host_link_probe": (_int, [C.POINTER(_int), _int, C.c_size_t, _int, C.POINTER(_dbl)]),
+    "ec_host_link_probe_buffers": (_int, [C.POINTER(_int), _int, _vp, _vp, C.c_size_t, C.c_size_t, _int, C.POINTER(_dbl)]),
     "ec_tensor_stream_run_device": (_int, [_vp, _int, _dp, _i64, _i64, _dp, _dp, _i64, _i64, _i64]),
     "ec_pipeline_set_sm_margin": (_int, [_vp, _int]),
     "ec_pipeline_set_schedule": (_int, [_vp, _int, _int]),

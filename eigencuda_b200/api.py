@@ -425,6 +425,16 @@ def host_link_probe(devices="all", nbytes=256 << 20, reps=5):
     return {"h2d": out[0], "d2h": out[1], "bidir_each_way": out[2]}
 
 
+def host_link_probe_buffers(devices, host_in_ptr, host_out_ptr, bytes_per_device, piece_bytes=64 << 20, reps=2):
+    """The link ceiling measured on the caller's own pinned buffers (ec_host_link_probe_buffers): as
+    much unique host memory as the job itself touches.  host_out is overwritten."""
+    dev_arr, ndev = _device_list(devices)
+    out = (C.c_double * 3)()
+    check(lib.ec_host_link_probe_buffers(dev_arr, ndev, C.c_void_p(int(host_in_ptr)), C.c_void_p(int(host_out_ptr)),
+                                         int(bytes_per_device), int(piece_bytes), int(reps), out))
+    return {"h2d": out[0], "d2h": out[1], "bidir_each_way": out[2]}
+
+
 def plan_dgemm(m, n, k, batch=1, sm_count=148):
     """(tile, stream_k) the dispatcher's cost model picks: tile 1 = 128x128, 2 = 64x64, 3 = 64x32,
     4 = 32x32.  Needs no device (ec_plan_dgemm)."""

@@ -654,6 +654,18 @@ int ec_pick_stream_devices(const int *devices, int ndev, int *out_devices, int *
 int ec_host_link_probe(const int *devices, int ndev, size_t bytes, int reps, double *out_gbs) {
   return host_link_probe_impl(devices, ndev, bytes, reps, out_gbs);
 }
+int ec_host_link_probe_buffers(const int *devices, int ndev, const void *host_in, void *host_out,
+                               size_t bytes_per_device, size_t piece_bytes, int reps, double *out_gbs) {
+  if (!out_gbs) return fail(EC_ERR_ARG, "null out pointer");
+  out_gbs[0] = out_gbs[1] = out_gbs[2] = 0.0;
+  if (!host_in || !host_out || bytes_per_device == 0 || piece_bytes == 0 || reps <= 0)
+    return fail(EC_ERR_ARG, "bad probe arguments");
+  std::vector<int> devs;
+  int rc = device_list_or_all(devices, ndev, &devs);
+  if (rc) return rc;
+  if (!is_pinned_host(host_in) || !is_pinned_host(host_out)) return fail(EC_ERR_ARG, "the probe needs pinned host buffers");
+  return host_link_probe_user_impl(devs, (const char *)host_in, (char *)host_out, bytes_per_device, piece_bytes, reps, out_gbs);
+}
 
 // ---- host memory + synthetic data ----------------------------------------------------------
 

@@ -411,6 +411,78 @@ struct LinkProbe {
   }
 };
 
+// The same measurement on the CALLER's pinned buffers: device g streams its slice
+// [g * bytes_per_device, (g+1) * bytes_per_device) of `host_in` to the device and a device buffer
+// back into its slice of `host_out`, `piece` bytes per copy.  Unlike the small rotating buffers of
+// LinkProbe this touches as much unique host memory as the real job does, so the last-level cache of
+// the host (which DMA reads can hit and DMA writes can land in) does not flatter the figure: this is
+// the ceiling of the tensor stream itself -- its traffic without the products.
+int host_link_probe_user_impl(const std::vector<int> &devs, const char *host_in, char *host_out,
+                              size_t bytes_per_device, size_t piece, int reps, double *out_gbs) {
+  const int G = (int)devs.size();
+  struct Dev {
+    void *d_in = nullptr, *d_out = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+  };
+  std::vector<Dev> D(G);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  auto cleanup = [&] {
+    for (int g = 0; g < G; ++g) {
+      cudaSetDevice(devs[g]);
+      if (D[g].s_in) cudaStreamDestroy(D[g].s_in);
+      if (D[g].s_out) cudaStreamDestroy(D[g].s_out);
+      if (D[g].d_in) cudaFree(D[g].d_in);
+      if (D[g].d_out) cudaFree(D[g].d_out);
+    }
+    cudaSetDevice(prev);
+  };
+  int rc = EC_OK;
+#define PROBE_CUDA(call)                                                                          \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      rc = fail(EC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      cleanup();                                                                                  \
+      return rc;                                                                                  \
+    }                                                                                             \
+  } while (0)
+  for (int g = 0; g < G; ++g) {
+    PROBE_CUDA(cudaSetDevice(devs[g]));
+    PROBE_CUDA(cudaMalloc(&D[g].d_in, piece));
+    PROBE_CUDA(cudaMalloc(&D[g].d_out, piece));
+    PROBE_CUDA(cudaMemsetAsync(D[g].d_out, 0, piece, 0));
+    PROBE_CUDA(cudaStreamCreateWithFlags(&D[g].s_in, cudaStreamNonBlocking));
+    PROBE_CUDA(cudaStreamCreateWithFlags(&D[g].s_out, cudaStreamNonBlocking));
+    PROBE_CUDA(cudaDeviceSynchronize());
+  }
+  for (int mode = 0; mode < 3; ++mode) {
+    double best = 1e300;
+    for (int rep = 0; rep < reps; ++rep) {
+      const auto t0 = std::chrono::steady_clock::now();
+      for (size_t off = 0; off < bytes_per_device; off += piece) {
+        const size_t len = std::min(piece, bytes_per_device - off);
+        for (int g = 0; g < G; ++g) {
+          const size_t at = (size_t)g * bytes_per_device + off;
+          PROBE_CUDA(cudaSetDevice(devs[g]));
+          if (mode != 1) PROBE_CUDA(cudaMemcpyAsync(D[g].d_in, host_in + at, len, cudaMemcpyHostToDevice, D[g].s_in));
+          if (mode != 0) PROBE_CUDA(cudaMemcpyAsync(host_out + at, D[g].d_out, len, cudaMemcpyDeviceToHost, D[g].s_out));
+        }
+      }
+      for (int g = 0; g < G; ++g) {
+        PROBE_CUDA(cudaStreamSynchronize(D[g].s_in));
+        PROBE_CUDA(cudaStreamSynchronize(D[g].s_out));
+      }
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      best = std::min(best, dt);
+    }
+    out_gbs[mode] = (double)G * (double)bytes_per_device / best / 1e9;
+  }
+#undef PROBE_CUDA
+  cleanup();
+  return EC_OK;
+}
+
 int device_list_or_all(const int *devices, int ndev, std::vector<int> *devs) {
   if (ndev < 0 || (ndev > 0 && !devices)) return fail(EC_ERR_ARG, "bad device list");
   if (ndev == 0)

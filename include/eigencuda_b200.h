@@ -186,6 +186,14 @@ int64_t ec_plan_chunks(int64_t count, int64_t chunk, int ramp, int64_t *starts, 
  * out_gbs[0] = H2D only, [1] = D2H only, [2] = each direction while both run -- GB/s summed over
  * the devices.  ndev == 0 = every device. */
 int ec_host_link_probe(const int *devices, int ndev, size_t bytes, int reps, double *out_gbs);
+/* The same on the caller's own pinned buffers: device number g streams its slice
+ * [g * bytes_per_device, (g+1) * bytes_per_device) of host_in to the device and a device buffer
+ * back into its slice of host_out, piece_bytes per copy.  This touches as much unique host memory
+ * as the job itself, so the host's last-level cache (which DMA can read from and write into) does
+ * not flatter the figure as it can with the small rotating buffers above: it is the ceiling of
+ * the tensor stream proper -- its traffic without the products.  host_out is overwritten. */
+int ec_host_link_probe_buffers(const int *devices, int ndev, const void *host_in, void *host_out,
+                               size_t bytes_per_device, size_t piece_bytes, int reps, double *out_gbs);
 /* Leave `sms` streaming multiprocessors unused by the (persistent, register-filling) GEMM kernels
  * so that concurrent kernels -- NCCL's, during the panel broadcasts of the 2D-partitioned DGEMM --
  * can run underneath them instead of queueing behind them.  0 (default) = use every SM. */

@@ -774,6 +774,19 @@ def test_host_link_probe_reports_a_ceiling():
     assert all(5.0 < v < 500.0 for v in got.values()), got        # GB/s: PCIe Gen5 x16 / C2C territory
 
 
+def test_host_link_probe_on_caller_buffers():
+    nbytes = 96 << 20
+    a, b = ec.PinnedBuffer((nbytes // 8,)), ec.PinnedBuffer((nbytes // 8,))
+    g = ec.count_available_gpus()
+    got = ec.host_link_probe_buffers("all", a.ptr, b.ptr, nbytes // g // 8 * 8, 16 << 20, 2)
+    assert all(5.0 < v < 1000.0 for v in got.values()), got
+    pageable = np.zeros(1 << 20)
+    with pytest.raises(RuntimeError):
+        ec.host_link_probe_buffers([0], pageable.ctypes.data, b.ptr, 1 << 20)
+    a.close()
+    b.close()
+
+
 def test_tensor_stream_rejects_unusable_result_arrays(pipe):
     """caller-supplied outputs are validated, not written through."""
     n = 64
