@@ -42,6 +42,9 @@ struct TileCfg {
   static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_;
   static constexpr int MIN_CTAS = MIN_CTAS_;
   static constexpr bool REGSPLIT = REGSPLIT_;
+  // The register-rich one-CTA-per-SM tile overlaps a tile's C stores with the first k-iteration of
+  // the CTA's next tile (see "fused tile turn-around" in the kernel).
+  static constexpr bool FUSE_EPI = REGSPLIT_ && MIN_CTAS_ == 1;
   static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
   static constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N;
   static constexpr int THREADS = (CONSUMER_WARPS + (REGSPLIT ? 4 : 1)) * 32;
@@ -111,6 +114,7 @@ struct GemmParams {
   unsigned skew_limit_ns;
   int launch_parity;
   int pdl_trigger;         // where griddepcontrol.launch_dependents is issued: 0 never, 1 after the wait, 2 at kernel start, 3 before the first epilogue
+  int fuse_epilogue;       // 1: tiles with FUSE_EPI defer their C stores into the next tile's first k-iteration
   int sk_sms;              // SM count: CTAs b and b + sk_sms share an SM and get ADJACENT stream-K
                            // ranges, so their tile boundaries (epilogues) fall at different times
 };
@@ -507,6 +511,43 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
   auto own_ws = [&]() -> double * {
     return p.sk_workspace + ((size_t)gridDim.x + Schedule::sk_rank(p)) * (BM * BN) + threadIdx.x;
   };
+  double acc[MB][NB][2];
+  // Fused tile turn-around (FUSE_EPI): a finished interior tile with beta == 0 is not stored at
+  // once.  Its 128 KB would drain through the SM's store path at 64 B/clk -- 2 k clocks during
+  // which all eight consumer warps sit in the epilogue together and the DMMA pipe idles.  Instead
+  // the tile stays in the accumulators ("pending") and the FIRST k-iteration of the CTA's next
+  // segment is issued row-block pair by row-block pair: store the pair's 16 x 32 results, clear
+  // those accumulators, issue the pair's 32 DMMAs of the new tile.  The stores of a tile thus
+  // spread over one k-iteration's worth of DMMA time (4 k clocks per SM), every accumulator still
+  // sees its k-steps in the same order (results are bit-identical), and no shared memory is spent.
+  bool pend = false;
+  double *pend_base = nullptr;
+  // stores of row blocks 2*ip, 2*ip+1 of the pending tile (beta == 0, interior: no predicates)
+  auto store_pair = [&](double *base, int ip) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double *pc = base + (int64_t)frag_mn<B_KMAJOR>(j, 2 * c + e) * p.ldc;
+        if (A_KMAJOR) {
+          pc += (g >> 1) + 4 * (g & 1);
+          pc[16 * ip] = p.alpha * acc[2 * ip][j][e];
+          pc[16 * ip + 8] = p.alpha * acc[2 * ip + 1][j][e];
+        } else {
+          pc += 2 * g;
+          double2 v;
+          v.x = p.alpha * acc[2 * ip][j][e];
+          v.y = p.alpha * acc[2 * ip + 1][j][e];
+          if (p.c_vec2) {
+            *reinterpret_cast<double2 *>(pc + 16 * ip) = v;
+          } else {
+            pc[16 * ip] = v.x;
+            pc[16 * ip + 1] = v.y;
+          }
+        }
+      }
+    }
+  };
   for (;;) {
     bool resume = false;
     if (sched.next_sk(sg)) {
@@ -539,8 +580,57 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
     } else {
       break;
     }
-    double acc[MB][NB][2];
-    if (resume) {
+    bool fused = false;
+    if (Cfg::FUSE_EPI && pend) {
+      pend = false;
+      if (!resume) {
+        fused = true;
+      } else {
+#pragma unroll
+        for (int ip = 0; ip < MB / 2; ++ip) store_pair(pend_base, ip);
+      }
+    }
+    if (Cfg::FUSE_EPI && fused) {
+      mbar_wait(full_bar(stage), phase);
+      if (pending_bar != 0) {   // deferred slot release, as in the main loop below
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pending_bar);
+      }
+      const uint32_t sA = smem_base + stage * STAGE_BYTES;
+      const uint32_t sB = sA + Cfg::A_BYTES;
+      double be[2][NB], bo[2][NB];
+      load_frags<B_KMAJOR, NB>(sB, wn0, 0, g, c, be[0], bo[0]);
+      load_frags<B_KMAJOR, NB>(sB, wn0, 8, g, c, be[1], bo[1]);
+#pragma unroll
+      for (int ip = 0; ip < MB / 2; ++ip) {
+        double ae[2][2], ao[2][2];
+        load_frags<A_KMAJOR, 2>(sA, wm0 + 16 * ip, 0, g, c, ae[0], ao[0]);
+        load_frags<A_KMAJOR, 2>(sA, wm0 + 16 * ip, 8, g, c, ae[1], ao[1]);
+        store_pair(pend_base, ip);
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+          for (int j = 0; j < NB; ++j) acc[2 * ip + ii][j][0] = acc[2 * ip + ii][j][1] = 0.0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+              dmma884(acc[2 * ip + ii][j][0], acc[2 * ip + ii][j][1], ae[h][ii], be[h][j]);
+#pragma unroll
+          for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+              dmma884(acc[2 * ip + ii][j][0], acc[2 * ip + ii][j][1], ao[h][ii], bo[h][j]);
+        }
+      }
+      pending_bar = empty_bar(stage);
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    } else if (resume) {
       const double *ws = own_ws();
 #pragma unroll
       for (int i = 0; i < MB; ++i)
@@ -555,7 +645,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
         for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     }
 
-    for (int kb = resume ? sg.kb1 : sg.kb0; kb < sg.kb1; ++kb) {
+    for (int kb = resume ? sg.kb1 : sg.kb0 + (fused ? 1 : 0); kb < sg.kb1; ++kb) {
       mbar_wait(full_bar(stage), phase);
       // Deferred slot release: the slot of the PREVIOUS k-iteration is handed back only now.
       // An arrive issued right behind the loads of its own stage carries no scoreboard wait,
@@ -685,6 +775,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
       // rows at compile-time offsets.  With an MN-major A the row blocks 2jb / 2jb+1 hold
       // adjacent rows 2g / 2g+1, so each pair goes out as one 16-byte store.
       double *base = Cb + (int64_t)(n0 + wn0) * p.ldc + (m0 + wm0);
+      if (Cfg::FUSE_EPI && p.fuse_epilogue && !use_beta) {
+        pend = true;   // stored underneath the first k-iteration of the next segment, or after the loop
+        pend_base = base;
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
 #pragma unroll
@@ -749,7 +844,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
       }
     }
   }
-
+  if (Cfg::FUSE_EPI && pend) {   // the CTA's last tile
+#pragma unroll
+    for (int ip = 0; ip < MB / 2; ++ip) store_pair(pend_base, ip);
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -123,6 +123,7 @@ int launch_tma_dmma(ec_pipeline *p, const CUtensorMap &tmA, const CUtensorMap &t
   gp.sk_flags = nullptr;
   gp.sk_epoch = 0;
   gp.pdl_trigger = p->pdl;
+  gp.fuse_epilogue = p->fuse_epilogue;
   // Is the GPU being shared?  The last persistent grid reported how far apart its CTAs started:
   // microseconds on an idle GPU, as long as the other kernel runs when some of them had to wait
   // for SMs it held.  A statically cut stream-K region then runs at the pace of the CTA that

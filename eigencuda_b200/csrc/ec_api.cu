@@ -75,6 +75,7 @@ static int pipeline_create_impl(int device, cudaStream_t external, bool use_exte
   ec_pipeline *p = new ec_pipeline();
   p->device = dev;
   if (const char *e = std::getenv("EC_DYNAMIC_TILES")) p->dynamic_tiles = std::atoi(e) != 0;
+  if (const char *e = std::getenv("EC_FUSE_EPILOGUE")) p->fuse_epilogue = std::atoi(e) != 0;
   if (const char *e = std::getenv("EC_PDL")) p->pdl = std::max(0, std::min(3, std::atoi(e)));
   p->sm_count = prop.multiProcessorCount;
   if (use_external) {
