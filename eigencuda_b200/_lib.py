@@ -87,6 +87,7 @@ SIGNATURES = {
     "ec_fill_uniform_block": (_int, [_vp, _u64, _u64, _dp, _i64, _i64, _i64, _i64, _i64, _i64]),
     "ec_pipeline_contention_events": (_i64, [_vp]),
     "ec_debug_hold_sms": (_int, [_int, _vp, _int, _i64]),
+    "ec_debug_fastdiv": (C.c_uint32, [C.c_uint32, C.c_uint32]),
     "ec_pipeline_launch_count": (_i64, [_vp]),
     "ec_pipeline_last_kernel": (C.c_char_p, [_vp]),
 }

@@ -24,6 +24,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef EC_FUSE_ROW_BLOCKS
+#define EC_FUSE_ROW_BLOCKS 2   // row blocks (of 8 rows) stored and restarted per step of the fused tile turn-around
+#endif
+
 namespace ec {
 
 // ------------------------------------------------------------------------------------------
@@ -81,6 +85,27 @@ using CfgN  = TileCfg<128,  16, 32, 16, 4, 3, false>;   // 4 consumer warps,  73
 // (A 128x64 / 2 CTAs-per-SM variant and register-split variants of the small tiles were measured
 //  and lost everywhere -- profiles/r01_tile_sweep*.json -- so they are not built.)
 
+// Division of a 31-bit dividend by an invariant divisor as one widening multiply and a shift
+// (Granlund-Montgomery: m = ceil(2^(31+l) / d), l = ceil(log2 d), fits 32 bits; q = n*m >> (31+l)
+// is exact for every n < 2^31).  A tile id is turned into (problem, tile row, tile column) on the
+// critical path twice per tile -- by the producer before its first load, by the consumers before
+// their stores -- and a 64-bit hardware-less division is a ~100-instruction dependent chain.
+struct FastDiv {
+  uint32_t m, sh, d;
+  __host__ __device__ __forceinline__ uint32_t div(uint32_t n) const {
+    return (uint32_t)(((uint64_t)n * m) >> sh);
+  }
+  static __host__ __device__ inline FastDiv make(uint32_t d) {
+    FastDiv f;
+    uint32_t l = 0;
+    while (l < 31 && (1u << l) < d) ++l;
+    f.sh = 31 + l;
+    f.m = (uint32_t)((((uint64_t)1 << f.sh) + d - 1) / d);
+    f.d = d;
+    return f;
+  }
+};
+
 struct GemmParams {
   int64_t M, N, K;
   int64_t batch;
@@ -114,6 +139,8 @@ struct GemmParams {
   unsigned skew_limit_ns;
   int launch_parity;
   int pdl_trigger;         // where griddepcontrol.launch_dependents is issued: 0 never, 1 after the wait, 2 at kernel start, 3 before the first epilogue
+  FastDiv fd_tiles_per_problem, fd_tiles_m;   // valid when total_tiles < 2^31 (fast_locate)
+  int fast_locate;
   int fuse_epilogue;       // 1: tiles with FUSE_EPI defer their C stores into the next tile's first k-iteration
   int sk_sms;              // SM count: CTAs b and b + sk_sms share an SM and get ADJACENT stream-K
                            // ranges, so their tile boundaries (epilogues) fall at different times
@@ -341,6 +368,25 @@ struct Schedule {
 // late or shares its SM with somebody else's kernel simply takes fewer tiles: the grid no longer
 // runs at the pace of its most delayed CTA.
 
+// tile id -> problem of the batch, tile row, tile column (m fastest)
+__device__ __forceinline__ void locate_tile(const GemmParams &p, int64_t tile, int tiles_per_problem,
+                                            int &b, int &tm, int &tn) {
+  if (p.fast_locate) {
+    const uint32_t t = (uint32_t)tile;
+    const uint32_t ub = p.fd_tiles_per_problem.div(t);
+    const uint32_t r = t - ub * (uint32_t)tiles_per_problem;
+    const uint32_t un = p.fd_tiles_m.div(r);
+    b = (int)ub;
+    tn = (int)un;
+    tm = (int)(r - un * (uint32_t)p.tiles_m);
+  } else {
+    b = (int)(tile / tiles_per_problem);
+    const int r = (int)(tile - (int64_t)b * tiles_per_problem);
+    tn = r / p.tiles_m;
+    tm = r - tn * p.tiles_m;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // The hot kernel
 // ------------------------------------------------------------------------------------------
@@ -408,13 +454,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
       if (p.stats && blockIdx.x == 0) p.stats[p.launch_parity ^ 1] = ~0ull;   // re-arm the next launch's slot
       int stage = 0;
       uint32_t phase = 0;
-      auto load_segment = [&](const Segment &sg) {
-        const int b = (int)(sg.tile / tiles_per_problem);
-        const int r = (int)(sg.tile - (int64_t)b * tiles_per_problem);
-        const int m0 = (r % p.tiles_m) * BM;
-        const int n0 = (r / p.tiles_m) * BN;
+      // (claim_kb, nxt: whole tiles only -- the CTA's next tile is claimed when the loads of this one
+      //  reach k-iteration claim_kb)
+      int64_t nxt = p.total_tiles;
+      auto load_segment = [&](const Segment &sg, int claim_kb, auto &&claim_next) {
+        int b, tm, tn;
+        locate_tile(p, sg.tile, tiles_per_problem, b, tm, tn);
+        const int m0 = tm * BM;
+        const int n0 = tn * BN;
         const int ba = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
         for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+          if (kb == claim_kb) nxt = claim_next();
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           const uint32_t sA = smem_base + stage * STAGE_BYTES;
@@ -429,9 +479,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
       };
       Schedule sched(p, kblocks);
       Segment sg;
-      while (sched.next_sk(sg)) load_segment(sg);
-      // whole tiles: the first one is fixed, further ones are claimed one tile ahead of their use
-      // (the round trip of the atomic hides behind the loads of the tile in between)
+      while (sched.next_sk(sg)) load_segment(sg, -1, [&]() -> int64_t { return 0; });
+      // Whole tiles: the first one is fixed, further ones are claimed while the last (up to) 8
+      // k-iterations of the tile before are being loaded: the round trip of the atomic hides behind
+      // those loads, and a CTA never sits on more than the tile it is loading.  (Round 2 first
+      // claimed a whole tile earlier -- two tiles at kernel start -- which let half the CTAs take
+      // every dynamic tile when there were exactly two whole tiles per CTA: n = 2816 and 3072 ran
+      // at 28 instead of 36 TFLOP/s, profiles/r02_sk_probe.txt.)
       const int64_t dyn_first = p.sk_tiles + (p.dp_all_dynamic ? 0 : (int64_t)gridDim.x);
       auto claim = [&]() -> int64_t {
         return dyn_first + (int64_t)(atomicAdd(p.dp_counter, 1ull) - p.dp_base);
@@ -442,8 +496,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
       const bool first_static = !p.dp_all_dynamic;
       const bool queued = p.dp_all_dynamic || p.total_tiles - p.sk_tiles > (int64_t)gridDim.x;
       int64_t cur = first_static ? p.sk_tiles + blockIdx.x : claim();
-      int64_t nxt = p.total_tiles;   // invalid
-      if (cur < p.total_tiles && queued) nxt = p.dp_counter ? claim() : cur + gridDim.x;
       int q = 0;
       uint32_t qphase = 0;
       for (bool first = first_static;; first = false) {
@@ -458,15 +510,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
           }
         }
         if (!valid) break;
-        int64_t nn = p.total_tiles;
-        if (nxt < p.total_tiles) nn = p.dp_counter ? claim() : nxt + gridDim.x;
         sg.tile = cur;
         sg.kb0 = 0;
         sg.kb1 = kblocks;
-        load_segment(sg);
+        nxt = p.total_tiles;   // invalid
+        load_segment(sg, queued ? (kblocks > 8 ? kblocks - 8 : 0) : -1,
+                     [&]() -> int64_t { return p.dp_counter ? claim() : cur + (int64_t)gridDim.x; });
         if (!queued) break;
         cur = nxt;
-        nxt = nn;
       }
       // Start-skew check, here where it delays nobody: this thread has nothing left to do.  A CTA
       // that started much later than the first one of the grid had to wait for an SM that some
@@ -601,28 +652,30 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
       double be[2][NB], bo[2][NB];
       load_frags<B_KMAJOR, NB>(sB, wn0, 0, g, c, be[0], bo[0]);
       load_frags<B_KMAJOR, NB>(sB, wn0, 8, g, c, be[1], bo[1]);
+      constexpr int R = (EC_FUSE_ROW_BLOCKS <= MB ? EC_FUSE_ROW_BLOCKS : MB);   // row blocks per step (even)
 #pragma unroll
-      for (int ip = 0; ip < MB / 2; ++ip) {
-        double ae[2][2], ao[2][2];
-        load_frags<A_KMAJOR, 2>(sA, wm0 + 16 * ip, 0, g, c, ae[0], ao[0]);
-        load_frags<A_KMAJOR, 2>(sA, wm0 + 16 * ip, 8, g, c, ae[1], ao[1]);
-        store_pair(pend_base, ip);
+      for (int ig = 0; ig < MB / R; ++ig) {
+        double ae[2][R], ao[2][R];
+        load_frags<A_KMAJOR, R>(sA, wm0 + 8 * R * ig, 0, g, c, ae[0], ao[0]);
+        load_frags<A_KMAJOR, R>(sA, wm0 + 8 * R * ig, 8, g, c, ae[1], ao[1]);
 #pragma unroll
-        for (int ii = 0; ii < 2; ++ii)
+        for (int q = 0; q < R / 2; ++q) store_pair(pend_base, (R / 2) * ig + q);
 #pragma unroll
-          for (int j = 0; j < NB; ++j) acc[2 * ip + ii][j][0] = acc[2 * ip + ii][j][1] = 0.0;
+        for (int ii = 0; ii < R; ++ii)
+#pragma unroll
+          for (int j = 0; j < NB; ++j) acc[R * ig + ii][j][0] = acc[R * ig + ii][j][1] = 0.0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
 #pragma unroll
-          for (int ii = 0; ii < 2; ++ii)
+          for (int ii = 0; ii < R; ++ii)
 #pragma unroll
             for (int j = 0; j < NB; ++j)
-              dmma884(acc[2 * ip + ii][j][0], acc[2 * ip + ii][j][1], ae[h][ii], be[h][j]);
+              dmma884(acc[R * ig + ii][j][0], acc[R * ig + ii][j][1], ae[h][ii], be[h][j]);
 #pragma unroll
-          for (int ii = 0; ii < 2; ++ii)
+          for (int ii = 0; ii < R; ++ii)
 #pragma unroll
             for (int j = 0; j < NB; ++j)
-              dmma884(acc[2 * ip + ii][j][0], acc[2 * ip + ii][j][1], ao[h][ii], bo[h][j]);
+              dmma884(acc[R * ig + ii][j][0], acc[R * ig + ii][j][1], ao[h][ii], bo[h][j]);
         }
       }
       pending_bar = empty_bar(stage);
@@ -764,10 +817,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
 
     // ---- epilogue: registers -> global, C = alpha*acc + beta*C ----
     if (p.pdl_trigger == 3) pdl_launch_dependents();
-    const int b = (int)(sg.tile / tiles_per_problem);
-    const int r = (int)(sg.tile - (int64_t)b * tiles_per_problem);
-    const int m0 = (r % p.tiles_m) * BM;
-    const int n0 = (r / p.tiles_m) * BN;
+    int b, tm, tn;
+    locate_tile(p, sg.tile, tiles_per_problem, b, tm, tn);
+    const int m0 = tm * BM;
+    const int n0 = tn * BN;
     double *Cb = p.C + (int64_t)b * p.stride_c;
     const bool use_beta = (p.beta != 0.0);
     if (m0 + BM <= p.M && n0 + BN <= p.N) {

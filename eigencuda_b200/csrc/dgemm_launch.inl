@@ -235,6 +235,9 @@ int run_tma_dmma(ec_pipeline *p, const Operand &oa, const Operand &ob, int64_t m
   gp.total_tiles = (int64_t)gp.tiles_m * gp.tiles_n * batch;
   gp.a_batched = (batch > 1 && stride_a != 0);
   gp.b_batched = (batch > 1 && stride_b != 0);
+  gp.fast_locate = gp.total_tiles < ((int64_t)1 << 31) ? 1 : 0;
+  gp.fd_tiles_per_problem = ec::FastDiv::make((uint32_t)std::max(1, gp.tiles_m * gp.tiles_n));
+  gp.fd_tiles_m = ec::FastDiv::make((uint32_t)std::max(1, gp.tiles_m));
   gp.c_vec2 = (((uintptr_t)C & 15u) == 0 && (ldc & 1) == 0 && (batch <= 1 || (stride_c & 1) == 0)) ? 1 : 0;
   int idx;
   if (oa.kmajor && ob.kmajor) { idx = 0; rc = launch_tma_dmma<Cfg, true, true>(p, tmA, tmB, gp, want_sk); }

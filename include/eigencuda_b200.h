@@ -282,6 +282,11 @@ int64_t ec_pipeline_contention_events(const ec_pipeline *p);
 /* Test hook: occupy `sms` streaming multiprocessors of `device` for `microseconds` with a kernel
  * that does nothing (one CTA per SM, sized so that no other CTA fits beside it), on `cuda_stream`. */
 int ec_debug_hold_sms(int device, void *cuda_stream, int sms, int64_t microseconds);
+/* Test hook; needs no device.  The kernels turn a tile id into (problem, tile row, tile column) with a
+ * multiply-and-shift division by an invariant divisor (FastDiv in csrc/dgemm_kernels.cuh); this returns
+ * what that routine gives for n / d (n < 2^31, 1 <= d < 2^31) so the CPU suite can check it against
+ * integer division. */
+uint32_t ec_debug_fastdiv(uint32_t n, uint32_t d);
 /* Launch counter: number of kernels this library has launched on this pipeline since creation. */
 int64_t ec_pipeline_launch_count(const ec_pipeline *p);
 /* Name of the kernel variant the last ec_dgemm* on this pipeline dispatched to. */

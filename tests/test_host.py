@@ -291,3 +291,23 @@ def test_chunk_plan_covers_the_tensor_with_short_ends():
                     assert sizes[-1] <= max(chunk // 8, 1) + 0 or sizes[-1] <= chunk // 2
                     assert max(sizes) == chunk
                     assert len(sizes) <= count // chunk + 7
+
+
+def test_fastdiv_matches_integer_division():
+    """The kernels locate a tile (problem, tile row, tile column) with a multiply-and-shift division by an
+    invariant divisor (FastDiv, csrc/dgemm_kernels.cuh; ec_debug_fastdiv runs the same routine on the host):
+    exact for every dividend below 2^31 and every divisor in [1, 2^31)."""
+    import random
+    from eigencuda_b200 import _lib
+    lib = _lib.load()
+    rng = random.Random(7)
+    top = (1 << 31) - 1
+    divisors = [1, 2, 3, 5, 7, 16, 17, 148, 641, 4096, 65535, 65536, 65537, (1 << 30) - 1, 1 << 30, (1 << 30) + 1, top]
+    divisors += [rng.randrange(1, 1 << rng.randrange(1, 32)) for _ in range(300)]
+    for d in divisors:
+        d = max(1, min(d, top))
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, top, top - 1, (top // d) * d, max(0, (top // d) * d - 1)]
+        ns += [rng.randrange(0, 1 << 31) for _ in range(40)]
+        for n in ns:
+            n = min(n, top)
+            assert lib.ec_debug_fastdiv(n, d) == n // d, (n, d)

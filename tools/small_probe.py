@@ -3,10 +3,10 @@ sys.path.insert(0, ".")
 import eigencuda_b200 as ec
 dev = torch.device("cuda", 0); stream = torch.cuda.current_stream()
 pipe = ec.CudaPipeline(0, stream=stream.cuda_stream)
-for n in (128, 192, 256, 384, 512, 640, 768, 896, 1024, 1280, 1536):
+for n in (128, 192, 256, 384, 512, 640, 768, 896, 1024, 1280, 1536, 1792, 2048, 2560, 3072, 4096):
     A = torch.randn(n*n, dtype=torch.float64, device=dev); B = torch.randn(n*n, dtype=torch.float64, device=dev); C = torch.empty(n*n, dtype=torch.float64, device=dev)
     row = []
-    for tile, sk in ((0, 1), (2, 0), (2, 2), (3, 0), (3, 2), (4, 0), (4, 2), (1, 2)):
+    for tile, sk in ((0, 1), (2, 0), (2, 2), (3, 0), (3, 2), (4, 0), (4, 2), (1, 0), (1, 2)):
         if tile: os.environ["EC_FORCE_TILE"] = str(tile)
         else: os.environ.pop("EC_FORCE_TILE", None)
         os.environ["EC_STREAM_K"] = str(sk)
