@@ -339,18 +339,18 @@ def test_fused_tile_turnaround_matches_plain_epilogue(monkeypatch):
     across all four operand layouts, multi-tile CTAs (persistent grid, stream-K region, dynamic
     claims), edge tiles next to interior ones, K of one k-iteration (the fused iteration is also the
     last) and beta != 0 (never deferred)."""
-    shapes = [  # (transa, transb, m, n, k, batch, beta)
-        (0, 0, 512, 512, 512, 40, 0.0), (1, 0, 512, 512, 512, 40, 0.0), (0, 1, 512, 512, 512, 40, 0.0),
-        (1, 1, 512, 512, 512, 40, 0.0), (0, 0, 4096, 4096, 256, 1, 0.0), (0, 0, 4000, 3000, 100, 1, 0.0),
-        (0, 0, 2048, 2048, 16, 2, 0.0), (0, 0, 2048, 2048, 8, 2, 0.0), (0, 0, 2304, 2304, 528, 1, 0.5),
-        (1, 0, 1536, 2560, 48, 3, 0.0)]
+    shapes = [  # (transa, transb, m, n, k, batch, beta, alpha); alpha == 1 skips the multiply in the fused stores
+        (0, 0, 512, 512, 512, 40, 0.0, 1.0), (1, 0, 512, 512, 512, 40, 0.0, 1.25), (0, 1, 512, 512, 512, 40, 0.0, 1.25),
+        (1, 1, 512, 512, 512, 40, 0.0, 1.0), (0, 0, 4096, 4096, 256, 1, 0.0, 1.25), (0, 0, 4000, 3000, 100, 1, 0.0, 1.0),
+        (0, 0, 2048, 2048, 16, 2, 0.0, 1.0), (0, 0, 2048, 2048, 8, 2, 0.0, 1.25), (0, 0, 2304, 2304, 528, 1, 0.5, 1.25),
+        (1, 0, 1536, 2560, 48, 3, 0.0, 1.0), (0, 0, 3072, 3072, 384, 1, 0.0, 1.0)]
     outs = {}
     for mode in ("1", "0"):
         monkeypatch.setenv("EC_FUSE_EPILOGUE", mode)
         monkeypatch.setenv("EC_FORCE_TILE", "1")
         p = ec.CudaPipeline(0)
         for key in shapes:
-            ta, tb, m, n, k, batch, beta = key
+            ta, tb, m, n, k, batch, beta, alpha = key
             A = rnd(51, ((k if ta else m) * batch, (m if ta else k)))
             B = rnd(52, ((n if tb else k), (k if tb else n)))
             C0 = rnd(53, (m * batch, n))
@@ -358,23 +358,23 @@ def test_fused_tile_turnaround_matches_plain_epilogue(monkeypatch):
             dA, dB = ec.CudaMatrix(A, p.get_stream()), ec.CudaMatrix(B, p.get_stream())
             dC = ec.CudaMatrix(C0, p.get_stream())
             if batch == 1:
-                p.dgemm(ta, tb, m, n, k, 1.25, dA.data(), lda, dB.data(), ldb, beta, dC.data(), m)
+                p.dgemm(ta, tb, m, n, k, alpha, dA.data(), lda, dB.data(), ldb, beta, dC.data(), m)
                 got = dC.to_eigen()
                 opA = A.T if ta else A
                 opB = B.T if tb else B
-                ref = 1.25 * orc.dgemm(np.asfortranarray(opA), np.asfortranarray(opB), flavour="fast") + beta * C0
+                ref = alpha * orc.dgemm(np.asfortranarray(opA), np.asfortranarray(opB), flavour="fast") + beta * C0
                 assert orc.rel_frobenius(got, ref) <= TOL, key
             else:
                 # problem i occupies rows [i*rows_a, (i+1)*rows_a) of the stacked A and rows [i*m, (i+1)*m) of C
                 rows_a = k if ta else m
-                p.dgemm_strided_batched(ta, tb, m, n, k, 1.25, dA.data(), lda, rows_a, dB.data(), ldb, 0, beta,
+                p.dgemm_strided_batched(ta, tb, m, n, k, alpha, dA.data(), lda, rows_a, dB.data(), ldb, 0, beta,
                                         dC.data(), m * batch, m, batch)
                 got = dC.to_eigen()
                 opB = B.T if tb else B
                 for i in (0, batch - 1):
                     Ai = A[i * rows_a:(i + 1) * rows_a, :]
                     opA = Ai.T if ta else Ai
-                    ref = 1.25 * orc.dgemm(np.asfortranarray(opA), np.asfortranarray(opB), flavour="fast") \
+                    ref = alpha * orc.dgemm(np.asfortranarray(opA), np.asfortranarray(opB), flavour="fast") \
                         + beta * C0[i * m:(i + 1) * m, :]
                     assert orc.rel_frobenius(got[i * m:(i + 1) * m, :], ref) <= TOL, (key, i)
             outs.setdefault(key, []).append(got)
