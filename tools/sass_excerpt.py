@@ -47,13 +47,20 @@ for n, body in funcs.items():
 print()
 
 
-def excerpt(pattern, key, before, after, title):
+def excerpt(pattern, key, before, after, title, last_cluster=False):
     for n, body in funcs.items():
         d = demangle(n)
         if re.search(pattern, d):
             idx = [i for i, l in enumerate(body) if mnemonic(l).startswith(key)]
             if not idx:
                 continue
+            if last_cluster:   # start of the last run of `key` instructions (gaps of at most 40 instructions)
+                start = idx[-1]
+                for a, b in zip(reversed(idx[:-1]), reversed(idx[1:])):
+                    if b - a > 40:
+                        break
+                    start = a
+                idx = [start]
             lo, hi = max(0, idx[0] - before), min(len(body), idx[0] + after)
             print(f"## {title}\n# {d[:200]}\n# first {key} at instruction {idx[0]} of {len(body)}")
             for l in body[lo:hi]:
@@ -63,7 +70,8 @@ def excerpt(pattern, key, before, after, title):
 
 
 excerpt(r"dgemm_tma_dmma_kernel<ec::TileCfg<128, 128.*false, false>", "UTMALDG", 12, 14, "FP64 hot kernel, producer: TMA loads signalled on mbarriers")
-excerpt(r"dgemm_tma_dmma_kernel<ec::TileCfg<128, 128.*false, false>", "DMMA", 14, 34, "FP64 hot kernel, consumer main loop: LDS.128 fragments feeding DMMA.8x8x4")
+excerpt(r"dgemm_tma_dmma_kernel<ec::TileCfg<128, 128.*false, true>", "DMMA", 30, 24, "FP64 hot kernel (NN), fused tile turn-around: DMUL + STG.E.128 of the finished tile, then the new tile's DMMAs with RZ as C")
+excerpt(r"dgemm_tma_dmma_kernel<ec::TileCfg<128, 128.*false, true>", "DMMA", 40, 30, "FP64 hot kernel (NN), consumer main loop: mbarrier wait, deferred release, LDS.128 fragments feeding DMMA.8x8x4", last_cluster=True)
 excerpt(r"dgemm_tma_dmma_kernel<ec::TileCfg<128, 128.*false, false>", "PREEXIT", 2, 4, "FP64 hot kernel, programmatic dependent launch (griddepcontrol)")
 excerpt(r"dgemm_tma_dmma_kernel<ec::TileCfg<128, 16", "DMMA", 10, 20, "128x16 tile (skinny products)")
 excerpt(r"ozaki_gemm_kernel", "UTCIMMA", 10, 16, "Ozaki int8 backend: tcgen05.mma.kind::i8 (UTCIMMA)")
