@@ -141,6 +141,7 @@ struct GemmParams {
   int pdl_trigger;         // where griddepcontrol.launch_dependents is issued: 0 never, 1 after the wait, 2 at kernel start, 3 before the first epilogue
   FastDiv fd_tiles_per_problem, fd_tiles_m;   // valid when total_tiles < 2^31 (fast_locate)
   int fast_locate;
+  int fuse_epilogue_wanted; // host side only: the pipeline's setting, read before the launch fills fuse_epilogue
   int fuse_epilogue;       // 1: tiles with FUSE_EPI defer their C stores into the next tile's first k-iteration
   int sk_sms;              // SM count: CTAs b and b + sk_sms share an SM and get ADJACENT stream-K
                            // ranges, so their tile boundaries (epilogues) fall at different times
@@ -390,10 +391,12 @@ __device__ __forceinline__ void locate_tile(const GemmParams &p, int64_t tile, i
 // ------------------------------------------------------------------------------------------
 // The hot kernel
 // ------------------------------------------------------------------------------------------
-template <class Cfg, bool A_KMAJOR, bool B_KMAJOR>
-__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
-    dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap tmA,
-                          const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+// (FUSE_EDGE: the fused tile turn-around also takes tiles that hang over the edge of C, with predicated
+//  element stores.  A second instantiation rather than a run-time branch: the branch alone costs the
+//  all-interior headline launch 0.2 % -- one more place where ptxas' schedule of the fused iteration moves.)
+template <class Cfg, bool A_KMAJOR, bool B_KMAJOR, bool FUSE_EDGE>
+__device__ __forceinline__ void dgemm_tma_dmma_body(const CUtensorMap &tmA, const CUtensorMap &tmB,
+                                                    const GemmParams &p) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
   constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS, STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
@@ -574,7 +577,29 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
   bool pend = false;
   double *pend_base = nullptr;
   // stores of row blocks 2*ip, 2*ip+1 of the pending tile (beta == 0, interior: no predicates)
+  bool pend_edge = false;             // the pending tile hangs over the edge of C (FUSE_EDGE only)
+  int pend_rows = 0, pend_cols = 0;   // rows / columns of C left from this warp's corner of the pending tile
   auto store_pair = [&](double *base, int ip) {
+    if constexpr (FUSE_EDGE) {
+      if (pend_edge) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = frag_mn<B_KMAJOR>(j, 2 * c + e);
+            if (col < pend_cols) {
+              double *pc = base + (int64_t)col * p.ldc;
+#pragma unroll
+              for (int ii = 0; ii < 2; ++ii) {
+                const int row = frag_mn<A_KMAJOR>(2 * ip + ii, g);
+                if (row < pend_rows) pc[row] = p.alpha * acc[2 * ip + ii][j][e];
+              }
+            }
+          }
+        }
+        return;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
 #pragma unroll
@@ -823,7 +848,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
     const int n0 = tn * BN;
     double *Cb = p.C + (int64_t)b * p.stride_c;
     const bool use_beta = (p.beta != 0.0);
-    if (m0 + BM <= p.M && n0 + BN <= p.N) {
+    const bool interior = m0 + BM <= p.M && n0 + BN <= p.N;
+    if (Cfg::FUSE_EPI && FUSE_EDGE && !interior && p.fuse_epilogue && !use_beta) {
+      // edge tile, deferred like an interior one (e.g. 15 of the 64 tiles of a 1000 x 1000 matrix)
+      pend = true;
+      pend_base = Cb + (int64_t)(n0 + wn0) * p.ldc + (m0 + wm0);
+      pend_edge = true;
+      pend_rows = (int)(p.M - (m0 + wm0));
+      pend_cols = (int)(p.N - (n0 + wn0));
+      continue;
+    }
+    if (interior) {
       // Interior tile (CTA-uniform branch): no predicates, one base pointer per fragment column,
       // rows at compile-time offsets.  With an MN-major A the row blocks 2jb / 2jb+1 hold
       // adjacent rows 2g / 2g+1, so each pair goes out as one 16-byte store.
@@ -831,6 +866,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
       if (Cfg::FUSE_EPI && p.fuse_epilogue && !use_beta) {
         pend = true;   // stored underneath the first k-iteration of the next segment, or after the loop
         pend_base = base;
+        if (FUSE_EDGE) pend_edge = false;
         continue;
       }
 #pragma unroll
@@ -901,6 +937,20 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
 #pragma unroll
     for (int ip = 0; ip < MB / 2; ++ip) store_pair(pend_base, ip);
   }
+}
+
+template <class Cfg, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
+    dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap tmA,
+                          const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  dgemm_tma_dmma_body<Cfg, A_KMAJOR, B_KMAJOR, false>(tmA, tmB, p);
+}
+// the same for products whose C has partial tiles (128x128 tile only)
+template <class Cfg, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
+    dgemm_tma_dmma_edge_kernel(const __grid_constant__ CUtensorMap tmA,
+                               const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  dgemm_tma_dmma_body<Cfg, A_KMAJOR, B_KMAJOR, Cfg::FUSE_EPI>(tmA, tmB, p);
 }
 
 // ------------------------------------------------------------------------------------------

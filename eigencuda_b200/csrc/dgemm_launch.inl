@@ -90,9 +90,15 @@ int ensure_sched_words(ec_pipeline *p) {
 }
 
 // Resident CTAs per SM of one kernel instantiation on one device (cached).
-template <class Cfg, bool AK, bool BK_>
+template <class Cfg, bool AK, bool BK_, bool EDGE>
+auto pick_tma_dmma_kernel() {
+  if constexpr (EDGE) return ec::dgemm_tma_dmma_edge_kernel<Cfg, AK, BK_>;
+  else return ec::dgemm_tma_dmma_kernel<Cfg, AK, BK_>;
+}
+
+template <class Cfg, bool AK, bool BK_, bool EDGE>
 int ctas_per_sm(ec_pipeline *p, int *out) {
-  auto kern = ec::dgemm_tma_dmma_kernel<Cfg, AK, BK_>;
+  auto kern = pick_tma_dmma_kernel<Cfg, AK, BK_, EDGE>();
   static std::atomic<int> cached[64];
   int v = cached[p->device & 63].load();
   if (v == 0) {
@@ -107,12 +113,17 @@ int ctas_per_sm(ec_pipeline *p, int *out) {
   return EC_OK;
 }
 
-template <class Cfg, bool AK, bool BK_>
+template <class Cfg, bool AK, bool BK_, bool EDGE = false>
 int launch_tma_dmma(ec_pipeline *p, const CUtensorMap &tmA, const CUtensorMap &tmB,
                     ec::GemmParams &gp, bool want_sk) {
-  auto kern = ec::dgemm_tma_dmma_kernel<Cfg, AK, BK_>;
+  // 128x128 tile and a C with partial tiles: the instantiation whose fused turn-around takes edge tiles too
+  if constexpr (Cfg::FUSE_EPI && !EDGE) {
+    if (gp.fuse_epilogue_wanted && gp.beta == 0.0 && (gp.M % Cfg::BM != 0 || gp.N % Cfg::BN != 0))
+      return launch_tma_dmma<Cfg, AK, BK_, true>(p, tmA, tmB, gp, want_sk);
+  }
+  auto kern = pick_tma_dmma_kernel<Cfg, AK, BK_, EDGE>();
   int ctas = 1;
-  int rc = ctas_per_sm<Cfg, AK, BK_>(p, &ctas);
+  int rc = ctas_per_sm<Cfg, AK, BK_, EDGE>(p, &ctas);
   if (rc) return rc;
   const int64_t slots = (int64_t)(p->sm_count - p->sm_margin) * ctas;
   const int64_t kblocks = (gp.K + ec::BK - 1) / ec::BK;
@@ -238,6 +249,7 @@ int run_tma_dmma(ec_pipeline *p, const Operand &oa, const Operand &ob, int64_t m
   gp.fast_locate = gp.total_tiles < ((int64_t)1 << 31) ? 1 : 0;
   gp.fd_tiles_per_problem = ec::FastDiv::make((uint32_t)std::max(1, gp.tiles_m * gp.tiles_n));
   gp.fd_tiles_m = ec::FastDiv::make((uint32_t)std::max(1, gp.tiles_m));
+  gp.fuse_epilogue_wanted = p->fuse_epilogue;
   gp.c_vec2 = (((uintptr_t)C & 15u) == 0 && (ldc & 1) == 0 && (batch <= 1 || (stride_c & 1) == 0)) ? 1 : 0;
   int idx;
   if (oa.kmajor && ob.kmajor) { idx = 0; rc = launch_tma_dmma<Cfg, true, true>(p, tmA, tmB, gp, want_sk); }

@@ -337,13 +337,16 @@ def test_fused_tile_turnaround_matches_plain_epilogue(monkeypatch):
     tile (row-block pair by row-block pair: store, clear, DMMA).  Every accumulator still sees its
     k-steps in the same order, so the bits must equal the plain epilogue's (EC_FUSE_EPILOGUE=0) --
     across all four operand layouts, multi-tile CTAs (persistent grid, stream-K region, dynamic
-    claims), edge tiles next to interior ones, K of one k-iteration (the fused iteration is also the
+    claims), edge tiles next to interior ones (deferred as well, by the kernel instantiation with predicated stores), K of one k-iteration (the fused iteration is also the
     last) and beta != 0 (never deferred)."""
     shapes = [  # (transa, transb, m, n, k, batch, beta, alpha); alpha == 1 skips the multiply in the fused stores
         (0, 0, 512, 512, 512, 40, 0.0, 1.0), (1, 0, 512, 512, 512, 40, 0.0, 1.25), (0, 1, 512, 512, 512, 40, 0.0, 1.25),
         (1, 1, 512, 512, 512, 40, 0.0, 1.0), (0, 0, 4096, 4096, 256, 1, 0.0, 1.25), (0, 0, 4000, 3000, 100, 1, 0.0, 1.0),
         (0, 0, 2048, 2048, 16, 2, 0.0, 1.0), (0, 0, 2048, 2048, 8, 2, 0.0, 1.25), (0, 0, 2304, 2304, 528, 1, 0.5, 1.25),
-        (1, 0, 1536, 2560, 48, 3, 0.0, 1.0), (0, 0, 3072, 3072, 384, 1, 0.0, 1.0)]
+        (1, 0, 1536, 2560, 48, 3, 0.0, 1.0), (0, 0, 3072, 3072, 384, 1, 0.0, 1.0),
+        # partial tiles: the edge instantiation defers them too (predicated stores), odd M / odd N included
+        (0, 0, 1000, 1000, 1000, 6, 0.0, 1.0), (1, 0, 1001, 999, 320, 1, 0.0, 1.25), (0, 1, 1000, 999, 200, 2, 0.0, 1.0),
+        (1, 1, 130, 4100, 64, 1, 0.0, 1.0)]
     outs = {}
     for mode in ("1", "0"):
         monkeypatch.setenv("EC_FUSE_EPILOGUE", mode)
