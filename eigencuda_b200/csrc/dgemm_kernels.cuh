@@ -346,6 +346,8 @@ struct Schedule {
   }
   __device__ __forceinline__ Schedule(const GemmParams &p, int kblocks_) {
     kblocks = kblocks_;
+    sk_it = sk_end = 0;
+    if (p.sk_tiles == 0) return;   // no stream-K region: keep three integer divisions off the start of every kernel
     const int64_t S = p.sk_tiles * kblocks;
     const unsigned rank = sk_rank(p);
     sk_it = S * rank / gridDim.x;
