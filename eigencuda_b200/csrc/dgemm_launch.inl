@@ -134,7 +134,12 @@ int launch_tma_dmma(ec_pipeline *p, const CUtensorMap &tmA, const CUtensorMap &t
   gp.sk_flags = nullptr;
   gp.sk_epoch = 0;
   gp.pdl_trigger = p->pdl;
-  gp.fuse_epilogue = p->fuse_epilogue;
+  // One-k-iteration tiles whose operands stream from HBM keep the plain epilogue: deferred stores go out only once the NEXT
+  // tile's first (and only) stage has landed, and that wait is then the whole tile (2^20 x 128 x 16: 5.07 TB/s plain, 4.24 fused;
+  // with L2-resident operands -- 8192 x 8192 x 16 -- fused wins like everywhere else: tools/fuse_k_probe.py,
+  // profiles/r02_fuse_k_probe.txt).
+  const bool operands_in_l2 = (double)(gp.M + gp.N) * (double)gp.K * 8.0 * (double)std::max<int64_t>(1, gp.batch) <= 48e6;
+  gp.fuse_epilogue = (p->fuse_epilogue && (kblocks >= p->fuse_min_kblocks || operands_in_l2)) ? 1 : 0;
   // Is the GPU being shared?  The last persistent grid reported how far apart its CTAs started:
   // microseconds on an idle GPU, as long as the other kernel runs when some of them had to wait
   // for SMs it held.  A statically cut stream-K region then runs at the pace of the CTA that

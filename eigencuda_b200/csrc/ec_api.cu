@@ -76,6 +76,7 @@ static int pipeline_create_impl(int device, cudaStream_t external, bool use_exte
   p->device = dev;
   if (const char *e = std::getenv("EC_DYNAMIC_TILES")) p->dynamic_tiles = std::atoi(e) != 0;
   if (const char *e = std::getenv("EC_FUSE_EPILOGUE")) p->fuse_epilogue = std::atoi(e) != 0;
+  if (const char *e = std::getenv("EC_FUSE_MIN_KBLOCKS")) p->fuse_min_kblocks = std::max(1, std::atoi(e));
   if (const char *e = std::getenv("EC_PDL")) p->pdl = std::max(0, std::min(3, std::atoi(e)));
   p->sm_count = prop.multiProcessorCount;
   if (use_external) {

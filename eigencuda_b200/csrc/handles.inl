@@ -41,6 +41,7 @@ struct ec_pipeline {
   unsigned long long stats_launches = 0;       // launches that carried the start-skew check (slot parity)
   int contended_left = 0;                      // launches left in "the GPU is shared" mode
   int64_t contended_events = 0;                // how often that mode was entered
+  int fuse_min_kblocks = 2;  // ... only for tiles of at least this many k-iterations, or L2-resident operands (EC_FUSE_MIN_KBLOCKS)
   int fuse_epilogue = 1;     // 128x128 tile: C stores ride under the next tile's first k-iteration (EC_FUSE_EPILOGUE=0: plain epilogue)
   int pdl = 1;               // programmatic dependent launch of the GEMM kernels (EC_PDL=0 turns it off)
   // small direct-mapped cache of encoded tensor maps: the compat loop and every tensor-stream
