@@ -406,6 +406,15 @@ def plan_chunks(count, chunk, ramp=True):
     return list(buf)
 
 
+def nccl_version():
+    """(major, minor, patch) of the NCCL the multi-GPU entry points bind at run time (ec_nccl_version);
+    needs no device.  Raises EigenCudaError (EC_ERR_UNSUPPORTED) with the loader's reason when it cannot
+    be loaded."""
+    v = C.c_int()
+    check(lib.ec_nccl_version(C.byref(v)))
+    return v.value // 10000, v.value // 100 % 100, v.value % 100
+
+
 def pick_stream_devices(devices="all"):
     """The subset of `devices` the host streams through fastest, by measurement
     (ec_pick_stream_devices).  Returns (device list, GB/s each way of that set, GB/s of all)."""

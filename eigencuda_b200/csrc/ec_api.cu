@@ -637,6 +637,15 @@ int ec_plan_shard(int64_t count, int ndev, int idx, int64_t *lo, int64_t *hi) {
   return EC_OK;
 }
 
+int ec_nccl_version(int *version) {
+  if (!version) return fail(EC_ERR_ARG, "null out pointer");
+  *version = 0;
+  NcclApi *api = nccl_api();
+  if (!api->handle) return fail(EC_ERR_UNSUPPORTED, "NCCL is not available: %s", api->why.c_str());
+  EC_NCCL(api, api->GetVersion(version));
+  return EC_OK;
+}
+
 int ec_pick_stream_devices(const int *devices, int ndev, int *out_devices, int *out_ndev, double *out_gbs) {
   if (!out_devices || !out_ndev) return fail(EC_ERR_ARG, "null out pointer");
   std::vector<int> devs;

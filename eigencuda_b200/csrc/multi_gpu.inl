@@ -41,11 +41,17 @@ NcclApi *nccl_api() {
   static std::once_flag once;
   std::call_once(once, [] {
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
-    if (const char *e = std::getenv("EC_NCCL_LIB")) api.handle = dlopen(e, RTLD_NOW | RTLD_GLOBAL);
-    for (const char *n : names)
-      if (!api.handle) api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    const char *forced = std::getenv("EC_NCCL_LIB");   // when set, the only candidate
+    if (forced && *forced) {
+      api.handle = dlopen(forced, RTLD_NOW | RTLD_GLOBAL);
+    } else {
+      for (const char *n : names)
+        if (!api.handle) api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    }
     if (!api.handle) {
-      api.why = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found");
+      const char *why = dlerror();   // a second dlerror() call returns NULL: read it once
+      api.why = std::string("cannot load ") + (forced && *forced ? forced : "libnccl.so.2") + ": " +
+                (why ? why : "not found");
       return;
     }
     bool ok = true;

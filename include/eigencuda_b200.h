@@ -160,6 +160,12 @@ int ec_tensor_stream_run_device(ec_pipeline *p, int kind, const double *F_dev, i
 int ec_tensor_stream_run_multi(ec_pipeline *p, const int *devices, int ndev, int kind, const double *F,
                                int64_t f_rows, int64_t f_cols, const double *const *tensor,
                                double *const *results, int64_t count, int64_t t_rows, int64_t t_cols);
+/* Whether the multi-GPU entry points can run here; needs no device.  Binds libnccl.so.2 (or the
+ * library the environment variable EC_NCCL_LIB names -- then only that one is tried) the way
+ * ec_tensor_stream_run_multi and ec_dgemm_2d do and stores ncclGetVersion()'s code
+ * (major*10000 + minor*100 + patch) in *version.  EC_ERR_UNSUPPORTED, with the loader's reason in
+ * ec_last_error_string(), when the library or one of the symbols used is missing. */
+int ec_nccl_version(int *version);
 /* ndev value for ec_tensor_stream_run_multi: stream through the subset of the box's devices that
  * the host moves data to and from fastest, chosen by measurement (ec_pick_stream_devices). */
 enum { EC_DEVICES_AUTO = -1 };

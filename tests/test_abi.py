@@ -130,3 +130,38 @@ def test_cmake_package_builds_the_reference_test_and_is_findable(tmp_path):
     assert res.returncode == 0, res.stdout + res.stderr
     out = run(["ldd", str(cbuild / "consumer")]).stdout
     assert "libeigencuda_b200.so" in out and "cublas" not in out.lower()
+
+
+def _nccl_probe(env_extra):
+    """ec_nccl_version in a fresh process (the binding is made once per process)."""
+    code = ("import eigencuda_b200 as ec\n"
+            "try:\n"
+            "    print('ok', *ec.nccl_version())\n"
+            "except ec.EigenCudaError as e:\n"
+            "    print('err', e.code, e)\n")
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), **env_extra)
+    res = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stderr
+    return res.stdout.strip().splitlines()[-1]
+
+
+def test_nccl_is_bound_at_run_time_and_reports_a_missing_library():
+    """The multi-GPU entry points dlopen NCCL (csrc/multi_gpu.inl: nccl_api); a library that cannot be
+    loaded must come back as EC_ERR_UNSUPPORTED with the loader's reason, not as a crash."""
+    from eigencuda_b200._lib import EC_ERR_UNSUPPORTED, lib
+    assert lib.ec_nccl_version(None) != 0          # null out pointer: argument error
+    line = _nccl_probe({"EC_NCCL_LIB": "/nonexistent/libnccl.so.2"})
+    assert line.startswith(f"err {EC_ERR_UNSUPPORTED} "), line
+    assert "/nonexistent/libnccl.so.2" in line
+    # a library without the NCCL symbols is refused, naming a missing symbol
+    line = _nccl_probe({"EC_NCCL_LIB": "libm.so.6"})
+    assert line.startswith(f"err {EC_ERR_UNSUPPORTED} ") and "lacks nccl" in line, line
+    # the default candidates: present in this image through torch's bundled copy when torch is imported first
+    import glob
+    import importlib.util
+    spec = importlib.util.find_spec("nvidia.nccl")
+    cands = glob.glob(os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")) if spec else []
+    if not cands:
+        pytest.skip("no libnccl.so.2 to bind in this environment")
+    line = _nccl_probe({"EC_NCCL_LIB": cands[0]})
+    assert line.startswith("ok 2 "), line
