@@ -561,7 +561,15 @@ def main():
         torch.cuda.synchronize()
         host_barrier()
         if rank == 0:
-            e2e, e2e_pageable = e2e_legs(args, ec, orc, pipe, torch, dev, world, Fh)
+            # A leg that cannot run on this box (pinned memory refused, NCCL unavailable, ...) is reported
+            # in the line with the traceback on stderr instead of costing the whole line; a parity
+            # failure inside the leg is a SystemExit and still ends the run.
+            try:
+                e2e, e2e_pageable = e2e_legs(args, ec, orc, pipe, torch, dev, world, Fh)
+            except Exception as exc:
+                import traceback
+                traceback.print_exc()
+                e2e = {"error": repr(exc)[:500]}
         host_barrier()
 
     # ---- configs[4]: one large DGEMM 2D-partitioned over all N GPUs (rank 0 drives them) ----
@@ -570,7 +578,12 @@ def main():
         torch.cuda.synchronize()
         host_barrier()
         if rank == 0:
-            gemm2d = dgemm_2d_leg(ec, orc, world, n=args.n2d or None)
+            try:
+                gemm2d = dgemm_2d_leg(ec, orc, world, n=args.n2d or None)
+            except Exception as exc:   # as above: reported, not a reason to lose the line
+                import traceback
+                traceback.print_exc()
+                gemm2d = {"error": repr(exc)[:500]}
         host_barrier()
 
     # ---- configs[1]: square DGEMM sweep on one GPU (rank 0, N=1), cuBLAS beside it at every n ----
