@@ -291,7 +291,7 @@ int ec_debug_hold_sms(int device, void *cuda_stream, int sms, int64_t microsecon
 /* Test hook; needs no device.  The kernels turn a tile id into (problem, tile row, tile column) with a
  * multiply-and-shift division by an invariant divisor (FastDiv in csrc/dgemm_kernels.cuh); this returns
  * what that routine gives for n / d (n < 2^31, 1 <= d < 2^31) so the CPU suite can check it against
- * integer division. */
+ * integer division (0 for d = 0). */
 uint32_t ec_debug_fastdiv(uint32_t n, uint32_t d);
 /* Launch counter: number of kernels this library has launched on this pipeline since creation. */
 int64_t ec_pipeline_launch_count(const ec_pipeline *p);

@@ -165,3 +165,28 @@ def test_nccl_is_bound_at_run_time_and_reports_a_missing_library():
         pytest.skip("no libnccl.so.2 to bind in this environment")
     line = _nccl_probe({"EC_NCCL_LIB": cands[0]})
     assert line.startswith("ok 2 "), line
+
+
+def test_every_entry_point_survives_null_and_zero_arguments():
+    """No exported function may crash the caller's process on a null handle, a null pointer or zero sizes:
+    each one is called that way (in a child process, so that a crash is a test failure and not the end of the
+    run) and has to come back -- with an error code where the header promises one."""
+    code = r'''
+import ctypes as C
+import eigencuda_b200._lib as L
+for name, (res, args) in L.SIGNATURES.items():
+    vals = [0.0 if a is C.c_double else (None if (a is C.c_void_p or issubclass(a, C._Pointer)) else 0) for a in args]
+    r = getattr(L.lib, name)(*vals)
+    print(name, r, flush=True)
+print("survived")
+'''
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    res = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT)
+    assert res.returncode == 0 and res.stdout.strip().endswith("survived"), res.stdout[-400:] + res.stderr[-400:]
+    got = dict(line.split(" ", 1) for line in res.stdout.strip().splitlines()[:-1])
+    import eigencuda_b200._lib as L
+    for name in ("ec_gemm", "ec_dgemm", "ec_matrix_upload", "ec_tensor_stream_run", "ec_tensor_stream_run_multi",
+                 "ec_dgemm_2d", "ec_pipeline_create", "ec_grid_create", "ec_pick_stream_devices", "ec_nccl_version"):
+        assert int(got[name]) != L.EC_OK, name
+    for name in ("ec_pipeline_destroy", "ec_matrix_free", "ec_grid_destroy", "ec_dist_matrix_destroy", "ec_host_free"):
+        assert int(got[name]) == L.EC_OK, name        # destroying nothing is not an error (unique_ptr deleters do it)
