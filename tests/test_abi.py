@@ -190,3 +190,33 @@ print("survived")
         assert int(got[name]) != L.EC_OK, name
     for name in ("ec_pipeline_destroy", "ec_matrix_free", "ec_grid_destroy", "ec_dist_matrix_destroy", "ec_host_free"):
         assert int(got[name]) == L.EC_OK, name        # destroying nothing is not an error (unique_ptr deleters do it)
+
+
+def test_device_needing_entry_points_report_the_missing_gpu():
+    """No CPU fallback anywhere: on a machine without a GPU every entry point that needs one comes back with an
+    error code and a message, valid arguments notwithstanding."""
+    import numpy as np
+    import eigencuda_b200 as ec
+    from eigencuda_b200._lib import EC_OK, lib
+    if ec.count_available_gpus() > 0:
+        pytest.skip("a GPU is present")
+    a = np.zeros((4, 4), order="F")
+    h, out3, devs, ndev = C.c_void_p(), (C.c_double * 3)(), (C.c_int * 8)(), C.c_int()
+    calls = {
+        "ec_matrix_alloc": lambda: lib.ec_matrix_alloc(None, 4, 4, C.byref(h)),
+        "ec_matrix_create_from_host": lambda: lib.ec_matrix_create_from_host(None, a.ctypes.data, 4, 4, C.byref(h)),
+        "ec_host_alloc": lambda: lib.ec_host_alloc(1024, C.byref(h)),
+        "ec_host_register": lambda: lib.ec_host_register(a.ctypes.data, a.nbytes),
+        "ec_host_link_probe": lambda: lib.ec_host_link_probe(None, 0, 1 << 20, 1, out3),
+        "ec_pick_stream_devices": lambda: lib.ec_pick_stream_devices(None, 0, devs, C.byref(ndev), None),
+        "ec_grid_create": lambda: lib.ec_grid_create(None, 0, 0, 0, C.byref(h)),
+        "ec_dgemm_2d_host": lambda: lib.ec_dgemm_2d_host(None, 0, 4, 4, 4, a.ctypes.data, 4, a.ctypes.data, 4, a.ctypes.data, 4),
+    }
+    for name, call in calls.items():
+        assert call() != EC_OK, name
+        assert lib.ec_last_error_string(), name
+        assert not h.value, name
+    with pytest.raises(ec.EigenCudaError):
+        ec.dgemm_2d(a, a)
+    with pytest.raises(ec.EigenCudaError):
+        ec.host_link_probe()
