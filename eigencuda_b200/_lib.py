@@ -71,6 +71,7 @@ SIGNATURES = {
     "ec_plan_chunks": (_i64, [_i64, _i64, _int, C.POINTER(_i64), _i64]),
     "ec_nccl_version": (_int, [C.POINTER(_int)]),
     "ec_pick_stream_devices": (_int, [C.POINTER(_int), _int, C.POINTER(_int), C.POINTER(_int), C.POINTER(_dbl)]),
+    "ec_plan_panels": (_i64, [_i64, _int, _int, _i64, C.POINTER(_i64), _i64]),
     "ec_plan_shard": (_int, [_i64, _int, _int, C.POINTER(_i64), C.POINTER(_i64)]),
     "ec_host_link_probe": (_int, [C.POINTER(_int), _int, C.c_size_t, _int, C.POINTER(_dbl)]),
     "ec_host_link_probe_buffers": (_int, [C.POINTER(_int), _int, _vp, _vp, C.c_size_t, C.c_size_t, _int, C.POINTER(_dbl)]),

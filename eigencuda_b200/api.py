@@ -406,6 +406,16 @@ def plan_chunks(count, chunk, ramp=True):
     return list(buf)
 
 
+def plan_panels(k, P, Q, panel=0):
+    """k-panel boundaries of the 2D-partitioned DGEMM on a P x Q grid (ec_plan_panels); needs no device."""
+    n = lib.ec_plan_panels(int(k), int(P), int(Q), int(panel), None, 0)
+    if n < 0:
+        check(_lib.EC_ERR_ARG)
+    buf = (C.c_int64 * n)()
+    lib.ec_plan_panels(int(k), int(P), int(Q), int(panel), buf, n)
+    return list(buf)
+
+
 def nccl_version():
     """(major, minor, patch) of the NCCL the multi-GPU entry points bind at run time (ec_nccl_version);
     needs no device.  Raises EigenCudaError (EC_ERR_UNSUPPORTED) with the loader's reason when it cannot

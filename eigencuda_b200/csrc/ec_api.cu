@@ -630,6 +630,22 @@ int64_t ec_plan_chunks(int64_t count, int64_t chunk, int ramp, int64_t *starts, 
   return (int64_t)plan.size();
 }
 
+int64_t ec_plan_panels(int64_t k, int P, int Q, int64_t panel, int64_t *starts, int64_t cap) {
+  if (k < 0 || P <= 0 || Q <= 0 || panel < 0 || cap < 0 || (cap > 0 && !starts)) {
+    fail(EC_ERR_ARG, "bad panel planning query");
+    return -1;
+  }
+  const std::vector<std::pair<int64_t, int64_t>> panels = summa_panels(k, P, Q, panel > 0 ? panel : 4096);
+  int64_t n = 0;
+  if (n < cap) starts[n] = 0;
+  ++n;
+  for (const auto &pn : panels) {
+    if (n < cap) starts[n] = pn.second;
+    ++n;
+  }
+  return n;
+}
+
 int ec_plan_shard(int64_t count, int ndev, int idx, int64_t *lo, int64_t *hi) {
   if (!lo || !hi) return fail(EC_ERR_ARG, "null out pointer");
   if (count < 0 || ndev <= 0 || idx < 0 || idx >= ndev) return fail(EC_ERR_ARG, "bad shard query");

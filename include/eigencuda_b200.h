@@ -253,6 +253,13 @@ int ec_dgemm_2d(ec_grid *g, const ec_dist_matrix *A, const ec_dist_matrix *B, ec
 int ec_dgemm_2d_host(const int *devices, int ndev, int64_t m, int64_t n, int64_t k, const double *A, int64_t lda,
                      const double *B, int64_t ldb, double *C, int64_t ldc);
 
+/* Planning query; needs no device: the k-panels ec_dgemm_2d walks for inner dimension k on a P x Q grid with
+ * panel width `panel` (0 = the default, 4096).  Panels never straddle an ownership boundary of A's column
+ * blocks (Q parts) or B's row blocks (P parts), so each has one owning grid column and one owning grid row.
+ * Writes up to `cap` boundaries (panel t covers [starts[t], starts[t+1])) and returns how many there are
+ * (number of panels + 1; 1 for k = 0), -1 on error. */
+int64_t ec_plan_panels(int64_t k, int P, int Q, int64_t panel, int64_t *starts, int64_t cap);
+
 /* ---- host memory + synthetic data helpers ------------------------------------------------- */
 
 /* Pinned host allocation (what CHANGELOG.md:32 records the reference once defaulted to). */

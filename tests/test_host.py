@@ -311,3 +311,26 @@ def test_fastdiv_matches_integer_division():
         for n in ns:
             n = min(n, top)
             assert lib.ec_debug_fastdiv(n, d) == n // d, (n, d)
+
+
+def test_panel_plan_of_the_2d_dgemm_respects_ownership_on_every_grid():
+    """ec_plan_panels (csrc/dgemm_2d.inl: summa_panels): on every P x Q grid up to 4 x 8 -- more shapes than any box
+    offers -- the panels tile [0, k) exactly, none is wider than asked, and none straddles a boundary between two
+    column blocks of A (Q parts) or two row blocks of B (P parts): each panel has ONE owner column and ONE owner
+    row, which is what lets its broadcasts start from a single root."""
+    import eigencuda_b200 as ec
+    for P in (1, 2, 3, 4):
+        for Q in (1, 2, 3, 4, 8):
+            for k in (0, 1, 7, 100, 4096, 4097, 12289, 65536):
+                for panel in (0, 1, 64, 1000, 4096):
+                    starts = ec.plan_panels(k, P, Q, panel)
+                    width = panel or 4096
+                    assert starts[0] == 0 and starts[-1] == k
+                    assert all(0 < b - a <= width for a, b in zip(starts, starts[1:])) or k == 0
+                    cuts = {ec.plan_shard(k, Q, q)[0] for q in range(Q)} | {ec.plan_shard(k, P, p)[0] for p in range(P)}
+                    for a, b in zip(starts, starts[1:]):
+                        assert not any(a < c < b for c in cuts), (P, Q, k, panel, a, b)
+    # the headline case: n = 65536 on 2 x 4, panels of 4096 -> 16 panels, 4 per owner column, 8 per owner row
+    assert ec.plan_panels(65536, 2, 4, 4096) == list(range(0, 65536 + 1, 4096))
+    from eigencuda_b200._lib import lib
+    assert lib.ec_plan_panels(-1, 1, 1, 0, None, 0) == -1 and lib.ec_plan_panels(8, 0, 1, 0, None, 0) == -1
