@@ -20,7 +20,7 @@ for line in sass.splitlines():
     if m:
         name = m.group(1)
         funcs[name] = []
-    elif name and re.match(r"\s*/\*[0-9a-f]{4}\*/", line):
+    elif name and re.match(r"\s*/\*[0-9a-f]{4,}\*/", line):
         funcs[name].append(line.rstrip())
 
 
@@ -29,7 +29,7 @@ def demangle(n):
 
 
 def mnemonic(line):
-    m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
     return m.group(1) if m else ""
 
 
